@@ -1,0 +1,211 @@
+"""Host-side mirror of the `blokus` crate's game-state API (blokus/src/game.rs:91-312) over the C ABI.
+
+`GameBatch` is n games stepped in lockstep on one B200; `Game` is the n == 1 view with the reference's
+method names (reset / apply / place_piece / get_legal_tiles / get_board / get_score / get_payoff /
+is_terminal / is_player_active / get_board_state / current_player / history), so a test written against
+the reference's `Game` reads the same here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BkError, Lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GameBatch:
+    """n independent Game values resident in HBM (bk_env)."""
+
+    def __init__(self, n_games: int, device: int = 0, lib: Optional[Lib] = None, _handle=None):
+        self.lib = lib or _lib.default_lib()
+        self.n = int(n_games)
+        self.device = device
+        self._owned = _handle is None
+        if _handle is None:
+            self.lib.require_device()
+            h = C.c_void_p()
+            self.lib.check(self.lib.bk_env_create(self.n, device, C.byref(h)))
+            self._h = h
+        else:
+            self._h = C.c_void_p(_handle)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._owned:
+            self.lib.bk_env_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Game::reset / Clone ------------------------------------------------------------------
+    def reset(self):
+        self.lib.check(self.lib.bk_env_reset(self._h))
+
+    def clone(self) -> "GameBatch":
+        h = C.c_void_p()
+        self.lib.check(self.lib.bk_env_clone(self._h, C.byref(h)))
+        out = GameBatch.__new__(GameBatch)
+        out.lib, out.n, out.device, out._owned, out._h = self.lib, self.n, self.device, True, h
+        return out
+
+    # ---- Game::apply / place_piece -------------------------------------------------------------
+    def apply(self, tiles: Sequence[int], piece_to_finish: Optional[Sequence[int]] = None, strict: bool = True) -> np.ndarray:
+        """Game::apply for every game (tile < 0 skips a game). Returns per-game status."""
+        t = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(self.n))
+        f = None if piece_to_finish is None else np.ascontiguousarray(np.asarray(piece_to_finish, dtype=np.int32).reshape(self.n))
+        st = np.zeros(self.n, dtype=np.int32)
+        rc = self.lib.bk_env_apply(self._h, _ptr(t), None if f is None else _ptr(f), _ptr(st))
+        if rc < 0 and (strict or rc != _lib.ERR_ILLEGAL_MOVE):
+            self.lib.check(rc)
+        return st
+
+    def place_piece(self, p: Sequence[int], v: Sequence[int], o: Sequence[int], strict: bool = True) -> np.ndarray:
+        pa, va, oa = (np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(self.n)) for x in (p, v, o))
+        st = np.zeros(self.n, dtype=np.int32)
+        rc = self.lib.bk_env_place_piece(self._h, _ptr(pa), _ptr(va), _ptr(oa), _ptr(st))
+        if rc < 0 and (strict or rc != _lib.ERR_ILLEGAL_MOVE):
+            self.lib.check(rc)
+        return st
+
+    # ---- accessors -------------------------------------------------------------------------------
+    def _get(self, fn, shape, dtype, *extra):
+        out = np.zeros(shape, dtype=dtype)
+        self.lib.check(fn(self._h, *extra, _ptr(out)))
+        return out
+
+    def legal_mask(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_legal_mask, (self.n, 400), np.uint8)
+
+    def legal_rows(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_legal_rows, (self.n, 20), np.uint32)
+
+    def legal_tiles(self):
+        """Game::get_legal_tiles per game, ascending."""
+        m = self.legal_mask()
+        return [np.flatnonzero(m[g]).tolist() for g in range(self.n)]
+
+    def board(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_board, (self.n, 400), np.uint8)
+
+    def anchors(self, player: int = -1) -> np.ndarray:
+        return self._get(self.lib.bk_env_anchors, (self.n, 400), np.uint8, player)
+
+    def current_player(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_current_player, (self.n,), np.int32)
+
+    def is_terminal(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_is_terminal, (self.n,), np.int32).astype(bool)
+
+    def is_player_active(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_is_player_active, (self.n, 4), np.int32).astype(bool)
+
+    def scores(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_scores, (self.n, 4), np.int32)
+
+    def payoff(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_payoff, (self.n, 4), np.float32)
+
+    def board_state(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_board_state, (self.n, 5, 20, 20), np.uint8)
+
+    def pieces(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_pieces, (self.n, 4), np.uint32)
+
+    def last_piece_lens(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_last_piece_lens, (self.n, 4), np.int32)
+
+    def digest(self) -> np.ndarray:
+        return self._get(self.lib.bk_env_digest, (self.n,), np.uint64)
+
+    def history(self):
+        """Game::history per game: list of (player, tile)."""
+        cnt = np.zeros(self.n, dtype=np.int32)
+        pl = np.zeros((self.n, _lib.MAX_PLIES), dtype=np.int32)
+        tl = np.zeros((self.n, _lib.MAX_PLIES), dtype=np.int32)
+        self.lib.check(self.lib.bk_env_history(self._h, _ptr(cnt), _ptr(pl), _ptr(tl)))
+        return [list(zip(pl[g, : cnt[g]].tolist(), tl[g, : cnt[g]].tolist())) for g in range(self.n)]
+
+    # ---- lockstep random playouts (BASELINE.json configs 1-2) -------------------------------------
+    def playout(self, seed: int = 0, first_game_id: int = 0, max_plies: int = -1, flags: int = 0) -> dict:
+        """Play every game forward on the device (legal-move gen + seeded choice + apply per ply)."""
+        self.lib.check(self.lib.bk_env_playout(self._h, seed, first_game_id, max_plies, flags))
+        steps = np.zeros(self.n, dtype=np.int32)
+        hashes = np.zeros(self.n, dtype=np.uint64)
+        self.lib.check(self.lib.bk_env_playout_results(self._h, _ptr(steps), _ptr(hashes)))
+        ms = C.c_float(0)
+        self.lib.check(self.lib.bk_env_last_kernel_ms(self._h, C.byref(ms)))
+        ctr = np.zeros(3, dtype=np.uint64)
+        self.lib.check(self.lib.bk_env_playout_counters(self._h, _ptr(ctr)))
+        return {"steps": steps, "hash": hashes, "kernel_ms": ms.value, "total_steps": int(ctr[0]),
+                "movegens": int(ctr[1]), "lane_ops": int(ctr[2])}
+
+
+class Game:
+    """One game with the reference's `Game` method names (blokus/src/game.rs)."""
+
+    def __init__(self, device: int = 0, lib: Optional[Lib] = None, _batch: Optional[GameBatch] = None):
+        self._b = _batch if _batch is not None else GameBatch(1, device=device, lib=lib)
+
+    @staticmethod
+    def reset(device: int = 0, lib: Optional[Lib] = None) -> "Game":  # game.rs:102
+        return Game(device=device, lib=lib)
+
+    def clone(self) -> "Game":
+        return Game(_batch=self._b.clone())
+
+    def apply(self, tile: int, piece_to_finish: Optional[int] = None) -> None:  # game.rs:150
+        """Raises BkError("Invalid move ...") like the reference's Err — but leaves the game untouched."""
+        self._b.apply([tile], None if piece_to_finish is None else [piece_to_finish])
+
+    def place_piece(self, p: int, v: int, o: int) -> "Game":  # game.rs:116 (returns a NEW game)
+        ns = self.clone()
+        ns._b.place_piece([p], [v], [o])
+        return ns
+
+    def get_board(self) -> np.ndarray:  # game.rs:196
+        return self._b.board()[0]
+
+    def current_player(self) -> int:  # game.rs:225
+        return int(self._b.current_player()[0])
+
+    def get_current_anchors(self):  # game.rs:238
+        return set(np.flatnonzero(self._b.anchors(-1)[0]).tolist())
+
+    def get_legal_tiles(self):  # game.rs:242 (ascending here; arbitrary order in the reference)
+        return self._b.legal_tiles()[0]
+
+    def get_score(self):  # game.rs:247
+        return self._b.scores()[0].tolist()
+
+    def get_payoff(self):  # game.rs:252
+        return self._b.payoff()[0].tolist()
+
+    def is_terminal(self) -> bool:  # game.rs:275
+        return bool(self._b.is_terminal()[0])
+
+    def is_player_active(self, player: int) -> bool:  # game.rs:279
+        return bool(self._b.is_player_active()[0, player])
+
+    def get_board_state(self) -> np.ndarray:  # game.rs:283
+        return self._b.board_state()[0].astype(bool)
+
+    def get_current_player_pieces(self):  # game.rs:230 — ids of the remaining pieces, list order
+        mask = int(self._b.pieces()[0, self.current_player()])
+        return [i for i in range(21) if (mask >> i) & 1]
+
+    @property
+    def history(self):  # game.rs:94
+        return self._b.history()[0]
+
+
+__all__ = ["GameBatch", "Game", "BkError"]

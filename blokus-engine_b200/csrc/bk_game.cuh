@@ -1,0 +1,410 @@
+// bk_game.cuh — warp-per-game Blokus rules engine for sm_100a.
+//
+// One warp owns one game.  Lane r (0..19) holds row r of every 20x20 bitboard as a uint32 with
+// 20 live bits (bit c = column c); lanes 20..31 hold zeros.  Vertical neighbours come from
+// __shfl_up/down, horizontal ones from shifts; everything is integer ALU work on registers.
+//
+// What is restated (behaviour only — the reference is hash maps of placements on a byte board):
+//   Board::place_tile / is_valid_move      blokus/src/board.rs:62-141
+//   get_piece_moves/get_moves/get_tile_moves  blokus/src/game.rs:12-74
+//   Game::apply / advance_player            blokus/src/game.rs:150-223
+//   get_scores / get_payoff                 blokus/src/board.rs:155-181, game.rs:252-272
+//
+// Closed forms used, with own_p = player p's squares:
+//   restricted_p = occupied | adj4(own_p)            (byte bit 1<<(4+p) or an occupied cell)
+//   anchors_p    = (diag4(own_p) | start_p) & ~restricted_p
+// A turn is a sequence of single-tile applies; the set of placements still consistent with the
+// tiles T laid this turn is recomputed from the TURN-START boards (own_p minus T) every time:
+//   S = { valid placements at turn start that contain T },  legal = union(cells(S)) \ T,
+// which is exactly what game.rs:156-173 maintains by set intersection.  The piece is committed
+// when legal becomes empty; then cells(S) == T, so the piece length is |T|.
+#pragma once
+#include <stdint.h>
+
+#include "bk_tables_gen.h"
+
+#define BK_FULL 0xffffffffu
+#define BK_ROWMASK 0xFFFFFu
+#define BK_HIST_CAP 360
+
+// Per-game record in HBM.  Lane r reads own[r] as one 16-byte vector: a warp's 20 loads are one
+// contiguous 320-byte segment.
+struct __align__(16) BkState {
+    uint32_t own[20][4];  // [row][player]
+    uint32_t legal[20];   // current legal-tile set (narrowed mid-piece), cached
+    uint32_t pieces[4];   // remaining piece-id masks
+    uint32_t meta;        // bits 0-1 current player, 2-5 eliminated mask, 6-8 |T|
+    uint32_t lastlens;    // byte p = last_piece_lens[p]            (game.rs:98)
+    uint32_t t01, t23;    // tiles laid this turn, 16 bits each (at most 4 are ever stored)
+    uint32_t ply;         // history length
+    uint32_t pad[3];
+};
+static_assert(sizeof(BkState) == 448, "BkState layout");
+
+struct BkRegs {
+    uint32_t o0, o1, o2, o3, legal;
+    uint32_t pc0, pc1, pc2, pc3;
+    uint32_t meta, lastlens, t01, t23, ply;
+};
+
+struct BkTabs {  // candidate table staged in shared memory
+    const uint32_t* w0;
+    const uint32_t* w1;
+    const uint32_t* w2;
+};
+
+struct BkCounters {  // lane-local partial sums, reduced once per kernel
+    uint32_t movegens;  // counted on lane 0 only
+    uint32_t crem;      // lane l < 21: sum over movegens of cells(piece l) if piece l was held
+};
+
+static __device__ const uint32_t g_cand_w0[BK_NUM_CANDS_PAD] = BK_CAND_W0_INIT;
+static __device__ const uint32_t g_cand_w1[BK_NUM_CANDS_PAD] = BK_CAND_W1_INIT;
+static __device__ const uint32_t g_cand_w2[BK_NUM_CANDS_PAD] = BK_CAND_W2_INIT;
+static __constant__ uint32_t c_cand_chunk_pieces[BK_NUM_CAND_CHUNKS] = BK_CAND_CHUNK_PIECES_INIT;
+static __constant__ uint8_t c_piece_points[BK_NUM_PIECES] = BK_PIECE_POINTS_INIT;
+static __constant__ uint8_t c_piece_first_variant[BK_NUM_PIECES + 1] = BK_PIECE_FIRST_VARIANT_INIT;
+static __constant__ uint8_t c_variant_width[BK_NUM_VARIANTS] = BK_VARIANT_WIDTH_INIT;
+static __constant__ uint8_t c_variant_height[BK_NUM_VARIANTS] = BK_VARIANT_HEIGHT_INIT;
+static __constant__ uint8_t c_variant_ncells[BK_NUM_VARIANTS] = BK_VARIANT_NCELLS_INIT;
+static __constant__ uint16_t c_variant_offsets[BK_NUM_VARIANTS][5] = BK_VARIANT_OFFSETS_INIT;
+
+#define BK_TABS_SMEM_WORDS (3 * BK_NUM_CANDS_PAD)
+
+// All threads of the CTA call this once; the caller must __syncthreads() afterwards.
+__device__ __forceinline__ BkTabs bk_stage_tables(uint32_t* smem) {
+    for (int i = threadIdx.x; i < BK_NUM_CANDS_PAD; i += blockDim.x) {
+        smem[i] = g_cand_w0[i];
+        smem[BK_NUM_CANDS_PAD + i] = g_cand_w1[i];
+        smem[2 * BK_NUM_CANDS_PAD + i] = g_cand_w2[i];
+    }
+    BkTabs t;
+    t.w0 = smem;
+    t.w1 = smem + BK_NUM_CANDS_PAD;
+    t.w2 = smem + 2 * BK_NUM_CANDS_PAD;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t bk_sel4(int p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return p == 0 ? a : (p == 1 ? b : (p == 2 ? c : d));
+}
+__device__ __forceinline__ uint32_t bk_smear4(uint32_t x) { uint32_t t = x | (x << 1); return t | (t << 2); }
+__device__ __forceinline__ uint32_t bk_smear5(uint32_t x) { uint32_t t = x | (x << 1); return t | (t << 2) | (x << 4); }
+
+__device__ __forceinline__ void bk_load(const BkState* __restrict__ s, int lane, BkRegs& G) {
+    if (lane < 20) {
+        const uint4 v = reinterpret_cast<const uint4*>(s->own)[lane];
+        G.o0 = v.x; G.o1 = v.y; G.o2 = v.z; G.o3 = v.w;
+        G.legal = s->legal[lane];
+    } else {
+        G.o0 = G.o1 = G.o2 = G.o3 = G.legal = 0u;
+    }
+    const uint4 pc = *reinterpret_cast<const uint4*>(s->pieces);
+    G.pc0 = pc.x; G.pc1 = pc.y; G.pc2 = pc.z; G.pc3 = pc.w;
+    const uint4 m = *reinterpret_cast<const uint4*>(&s->meta);
+    G.meta = m.x; G.lastlens = m.y; G.t01 = m.z; G.t23 = m.w;
+    G.ply = s->ply;
+}
+
+__device__ __forceinline__ void bk_store(BkState* __restrict__ s, int lane, const BkRegs& G) {
+    if (lane < 20) {
+        reinterpret_cast<uint4*>(s->own)[lane] = make_uint4(G.o0, G.o1, G.o2, G.o3);
+        s->legal[lane] = G.legal;
+    }
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(s->pieces) = make_uint4(G.pc0, G.pc1, G.pc2, G.pc3);
+        *reinterpret_cast<uint4*>(&s->meta) = make_uint4(G.meta, G.lastlens, G.t01, G.t23);
+        s->ply = G.ply;
+    }
+}
+
+__device__ __forceinline__ int bk_cur(const BkRegs& G) { return int(G.meta & 3u); }
+__device__ __forceinline__ uint32_t bk_elim(const BkRegs& G) { return (G.meta >> 2) & 0xFu; }
+__device__ __forceinline__ bool bk_terminal(const BkRegs& G) { return bk_elim(G) == 0xFu; }
+
+// free_p / anchors_p rows of this lane for player p (see header).
+__device__ __forceinline__ void bk_free_anchor(uint32_t mine, uint32_t occ, int p, int lane, uint32_t& free_,
+                                               uint32_t& anch) {
+    uint32_t up = __shfl_up_sync(BK_FULL, mine, 1);
+    uint32_t dn = __shfl_down_sync(BK_FULL, mine, 1);
+    if (lane == 0) up = 0u;
+    if (lane >= 19) dn = 0u;
+    const uint32_t ud = up | dn;
+    const uint32_t adj = (mine << 1) | (mine >> 1) | ud;
+    const uint32_t diag = (ud << 1) | (ud >> 1);
+    // board.rs:44-53: start corners 0, 19, 399, 380 for players 0..3
+    uint32_t start = 0u;
+    if (lane == ((p >> 1) ? 19 : 0)) start = (p == 1 || p == 2) ? (1u << 19) : 1u;
+    const uint32_t rowmask = lane < 20 ? BK_ROWMASK : 0u;
+    free_ = ~(occ | adj) & rowmask;
+    anch = (diag | start) & free_;
+}
+
+// Turn-start legal-tile board of a player: union of the cells of every valid placement of every
+// remaining piece (get_tile_moves keys, game.rs:60-74).  Fully unrolled over the 91 variants.
+__device__ __noinline__ uint32_t bk_movegen_rows(uint32_t bk_free, uint32_t bk_anch, uint32_t bk_pieces, int lane) {
+#include "bk_movegen_gen.inc"
+    return bk_legal & BK_ROWMASK;
+}
+
+__device__ __forceinline__ uint32_t bk_movegen_start(const BkRegs& G, int p, int lane, BkCounters& ctr) {
+    const uint32_t mine = bk_sel4(p, G.o0, G.o1, G.o2, G.o3);
+    const uint32_t occ = G.o0 | G.o1 | G.o2 | G.o3;
+    const uint32_t pieces = bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3);
+    uint32_t free_, anch;
+    bk_free_anchor(mine, occ, p, lane, free_, anch);
+    if (lane == 0) ctr.movegens += 1u;
+    if (lane < BK_NUM_PIECES && ((pieces >> lane) & 1u))
+        ctr.crem += uint32_t(c_piece_points[lane]) * uint32_t(c_piece_first_variant[lane + 1] - c_piece_first_variant[lane]);
+    if (pieces == 0u || !__any_sync(BK_FULL, anch != 0u)) return 0u;
+    return bk_movegen_rows(free_, anch, pieces, lane);
+}
+
+struct BkNarrow {
+    uint32_t legal;  // this lane's row of the narrowed legal set
+    int pid;         // piece id of a surviving placement (the committed piece when legal is empty)
+    bool any_valid;  // some turn-start placement contains T (always true after a legal tile)
+};
+
+// S = { turn-start-valid placements containing all nT tiles in T }, evaluated inside the 9x9 window
+// centred on T[0].  free_/anch are the TURN-START rows of this lane.
+__device__ __forceinline__ BkNarrow bk_narrow(uint32_t free_, uint32_t anch, uint32_t pieces, const int (&T)[5],
+                                              int nT, int lane, const BkTabs& tabs) {
+    const int tr = T[0] / 20, tc = T[0] % 20;
+    const uint32_t fs = ((free_ << 4) >> tc) & 0x1FFu;
+    const uint32_t as = ((anch << 4) >> tc) & 0x1FFu;
+    const int wr = lane - tr + 4;
+    const bool inw = (wr >= 0) && (wr < 9) && (lane < 20);
+    const int wk = inw ? wr / 3 : 3;
+    const int sh = inw ? 9 * (wr - 3 * wk) : 0;
+    const uint32_t FW0 = __reduce_or_sync(BK_FULL, wk == 0 ? fs << sh : 0u);
+    const uint32_t FW1 = __reduce_or_sync(BK_FULL, wk == 1 ? fs << sh : 0u);
+    const uint32_t FW2 = __reduce_or_sync(BK_FULL, wk == 2 ? fs << sh : 0u);
+    const uint32_t AW0 = __reduce_or_sync(BK_FULL, wk == 0 ? as << sh : 0u);
+    const uint32_t AW1 = __reduce_or_sync(BK_FULL, wk == 1 ? as << sh : 0u);
+    const uint32_t AW2 = __reduce_or_sync(BK_FULL, wk == 2 ? as << sh : 0u);
+    uint32_t TW0 = 0u, TW1 = 0u, TW2 = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        if (i < nT) {
+            const int r = T[i] / 20 - tr + 4, c = T[i] % 20 - tc + 4;
+            const int bit = r * 9 + c;
+            const int k = bit / 27;
+            const uint32_t b = 1u << (bit - 27 * k);
+            if (k == 0) TW0 |= b; else if (k == 1) TW1 |= b; else TW2 |= b;
+        }
+    }
+    uint32_t L0 = 0u, L1 = 0u, L2 = 0u;
+    int found = 0;
+#pragma unroll 1
+    for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
+        if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
+        const int idx = ch * 32 + lane;
+        const uint32_t w0 = tabs.w0[idx];
+        const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
+        const uint32_t pid = w0 >> 27;
+        const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
+        const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
+        const bool covers = (((m0 & TW0) ^ TW0) | ((m1 & TW1) ^ TW1) | ((m2 & TW2) ^ TW2)) == 0u;
+        if (((pieces >> pid) & 1u) && fits && hits && covers) {
+            L0 |= m0; L1 |= m1; L2 |= m2;
+            found = int(pid) + 1;
+        }
+    }
+    L0 = __reduce_or_sync(BK_FULL, L0) & ~TW0;
+    L1 = __reduce_or_sync(BK_FULL, L1) & ~TW1;
+    L2 = __reduce_or_sync(BK_FULL, L2) & ~TW2;
+    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+    BkNarrow out;
+    out.pid = found - 1;
+    out.any_valid = found > 0;
+    uint32_t row = 0u;
+    if (inw) {
+        const uint32_t Lw = wk == 0 ? L0 : (wk == 1 ? L1 : L2);
+        const uint32_t slice = (Lw >> sh) & 0x1FFu;
+        row = ((slice << tc) >> 4) & BK_ROWMASK;
+    }
+    out.legal = row;
+    return out;
+}
+
+__device__ __forceinline__ void bk_unpack_T(const BkRegs& G, int (&T)[5], int& nT) {
+    nT = int((G.meta >> 6) & 7u);
+    T[0] = int(G.t01 & 0xFFFFu); T[1] = int(G.t01 >> 16);
+    T[2] = int(G.t23 & 0xFFFFu); T[3] = int(G.t23 >> 16);
+    T[4] = 0;
+}
+
+// this lane's row of the mask of tiles laid this turn
+__device__ __forceinline__ uint32_t bk_T_row(const int (&T)[5], int nT, int lane) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (i < nT && T[i] / 20 == lane) m |= 1u << (T[i] % 20);
+    return m;
+}
+
+__device__ __forceinline__ int bk_nth_set_bit(uint32_t mask, int n) {  // n-th (0-based) set bit, -1 if none
+    if (n < 0 || n >= __popc(mask)) return -1;
+    return int(__fns(mask, 0u, n + 1));
+}
+
+// Game::advance_player (game.rs:203-223) as a loop: next seat that is not eliminated and has a
+// legal tile; seats found blocked are eliminated for good.  Move generation is skipped for seats
+// already eliminated — their set is provably empty (boards only fill up), so the result is the same.
+__device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr) {
+    uint32_t elim = bk_elim(G);
+    int cur = bk_cur(G);
+    uint32_t legal = 0u;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        if (elim == 0xFu) break;
+        cur = (cur + 1) & 3;
+        if ((elim >> cur) & 1u) continue;
+        const uint32_t lg = bk_movegen_start(G, cur, lane, ctr);
+        if (!__any_sync(BK_FULL, lg != 0u)) { elim |= 1u << cur; continue; }
+        legal = lg;
+        break;
+    }
+    G.legal = legal;
+    G.meta = (G.meta & ~0x3Fu) | uint32_t(cur) | (elim << 2);
+}
+
+// Game::apply(tile, piece_to_finish) (game.rs:150-194).  finish < 0 is None.  Returns false (and
+// leaves the game untouched) when the tile is not legal or finish is out of range.
+__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
+                                         BkCounters& ctr) {
+    if (tile < 0 || tile >= 400 || bk_terminal(G)) return false;
+    const int p = bk_cur(G);
+    const int tr = tile / 20, tc = tile % 20;
+    const uint32_t bit = (lane == tr) ? (1u << tc) : 0u;
+    if (!__any_sync(BK_FULL, (G.legal & bit) != 0u)) return false;
+    const uint32_t pieces = bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3);
+    int fin_pid = -1;
+    if (finish >= 0) {
+        fin_pid = bk_nth_set_bit(pieces, finish);
+        if (fin_pid < 0) return false;
+    }
+    int T[5], nT;
+    bk_unpack_T(G, T, nT);
+    T[nT] = tile;
+    nT += 1;
+    // Board::place_tile (board.rs:95-141): the square joins own_p; restricted/anchor sets are
+    // derived from the bitboards on demand.
+    if (p == 0) G.o0 |= bit; else if (p == 1) G.o1 |= bit; else if (p == 2) G.o2 |= bit; else G.o3 |= bit;
+    G.ply += 1u;
+    const uint32_t trow = bk_T_row(T, nT, lane);
+    const uint32_t mine0 = bk_sel4(p, G.o0, G.o1, G.o2, G.o3) & ~trow;
+    const uint32_t occ0 = (G.o0 | G.o1 | G.o2 | G.o3) & ~trow;
+    uint32_t free_, anch;
+    bk_free_anchor(mine0, occ0, p, lane, free_, anch);
+    const BkNarrow nw = bk_narrow(free_, anch, pieces, T, nT, lane, tabs);
+    const bool done = !__any_sync(BK_FULL, nw.legal != 0u);
+    if (done || fin_pid >= 0) {
+        // game.rs:176-191: commit the piece, remember its size, pass the turn
+        const int pid = fin_pid >= 0 ? fin_pid : nw.pid;
+        const uint32_t len = fin_pid >= 0 ? uint32_t(c_piece_points[pid]) : uint32_t(nT);
+        const uint32_t clr = ~(1u << pid);
+        if (p == 0) G.pc0 &= clr; else if (p == 1) G.pc1 &= clr; else if (p == 2) G.pc2 &= clr; else G.pc3 &= clr;
+        G.lastlens = (G.lastlens & ~(0xFFu << (8 * p))) | (len << (8 * p));
+        G.meta &= ~(7u << 6);
+        G.t01 = 0u; G.t23 = 0u;
+        bk_advance(G, lane, ctr);
+    } else {
+        G.legal = nw.legal;
+        G.meta = (G.meta & ~(7u << 6)) | (uint32_t(nT) << 6);
+        G.t01 = uint32_t(T[0]) | (uint32_t(T[1]) << 16);
+        G.t23 = uint32_t(T[2]) | (uint32_t(T[3]) << 16);
+    }
+    return true;
+}
+
+// Game::reset (game.rs:102-114)
+__device__ __forceinline__ void bk_reset(BkRegs& G, int lane, BkCounters& ctr) {
+    G.o0 = G.o1 = G.o2 = G.o3 = 0u;
+    G.pc0 = G.pc1 = G.pc2 = G.pc3 = (1u << BK_NUM_PIECES) - 1u;
+    G.meta = 0u; G.lastlens = 0u; G.t01 = 0u; G.t23 = 0u; G.ply = 0u;
+    G.legal = bk_movegen_start(G, 0, lane, ctr);
+}
+
+__device__ __forceinline__ int bk_warp_sum(int v) {
+    return int(__reduce_add_sync(BK_FULL, unsigned(v)));
+}
+
+// Board::get_scores (board.rs:155-181)
+__device__ __forceinline__ void bk_scores(const BkRegs& G, int (&sc)[4]) {
+    sc[0] = bk_warp_sum(__popc(G.o0)); sc[1] = bk_warp_sum(__popc(G.o1));
+    sc[2] = bk_warp_sum(__popc(G.o2)); sc[3] = bk_warp_sum(__popc(G.o3));
+    const uint32_t pcs[4] = {G.pc0, G.pc1, G.pc2, G.pc3};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        sc[p] -= 89;
+        if (pcs[p] == 0u) {
+            sc[p] += 15;
+            if (((G.lastlens >> (8 * p)) & 0xFFu) == 1u) sc[p] += 5;
+        }
+    }
+}
+
+// Game::get_payoff (game.rs:252-272)
+__device__ __forceinline__ void bk_payoff(const BkRegs& G, float (&pay)[4]) {
+    int sc[4];
+    bk_scores(G, sc);
+    int hi = sc[0];
+#pragma unroll
+    for (int p = 1; p < 4; ++p) hi = sc[p] > hi ? sc[p] : hi;
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) k += (sc[p] == hi) ? 1 : 0;
+    const float share = __fdiv_rn(1.0f, float(k));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) pay[p] = (sc[p] == hi) ? share : 0.0f;
+}
+
+__device__ __forceinline__ uint64_t bk_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Order-independent digest of the full game state (same word list as oracle/oracle_capi.cpp
+// state_digest): own rows, legal rows, remaining-piece masks, last piece lengths, seat + eliminated.
+__device__ __forceinline__ uint64_t bk_digest(const BkRegs& G, int lane) {
+    uint64_t s = 0ull;
+    if (lane < 20) {
+        s += bk_splitmix64((uint64_t(0 * 32 + lane) << 32) | G.o0);
+        s += bk_splitmix64((uint64_t(1 * 32 + lane) << 32) | G.o1);
+        s += bk_splitmix64((uint64_t(2 * 32 + lane) << 32) | G.o2);
+        s += bk_splitmix64((uint64_t(3 * 32 + lane) << 32) | G.o3);
+        s += bk_splitmix64((uint64_t(4 * 32 + lane) << 32) | G.legal);
+    }
+    if (lane < 4) {
+        s += bk_splitmix64((uint64_t(5 * 32 + lane) << 32) | bk_sel4(lane, G.pc0, G.pc1, G.pc2, G.pc3));
+        s += bk_splitmix64((uint64_t(6 * 32 + lane) << 32) | ((G.lastlens >> (8 * lane)) & 0xFFu));
+    }
+    if (lane == 0) s += bk_splitmix64((uint64_t(7 * 32) << 32) | (uint32_t(bk_cur(G)) | (bk_elim(G) << 4)));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(BK_FULL, s, d);
+    return s;
+}
+
+// number of legal tiles and the idx-th one in ascending tile order
+__device__ __forceinline__ int bk_legal_count(uint32_t legal) { return bk_warp_sum(__popc(legal)); }
+
+__device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane) {
+    const int cnt = __popc(legal);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(BK_FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int excl = incl - cnt;
+    const bool here = (idx >= excl) && (idx < incl);
+    int tile = 0;
+    if (here) tile = lane * 20 + int(__fns(legal, 0u, idx - excl + 1));
+    const unsigned who = __ballot_sync(BK_FULL, here);
+    return __shfl_sync(BK_FULL, tile, who ? (__ffs(who) - 1) : 0);
+}

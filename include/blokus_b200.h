@@ -1,0 +1,209 @@
+/* blokus_b200.h — C ABI of the B200-native Blokus self-play hot path.
+ *
+ * Drop-in boundary for the path SURVEY.md §8 names: the `blokus` crate's game-state API
+ * (blokus/src/game.rs:91-312, blokus/src/board.rs:18-206) and the `self_play` crate's MCTS /
+ * client interface (self_play/src/lib.rs:9-63, self_play/src/simulation.rs:14-296), batched over
+ * thousands of games that live in B200 HBM.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - Every call returns 0 on success or a negative bk_status; bk_last_error() returns a
+ *     thread-local UTF-8 message (the analogue of the reference's Err(String)).
+ *   - A handle is bound to one CUDA device and one stream and is not thread-safe; distinct handles
+ *     are independent (mirrors the reference's one-process-per-game model, model/training.py:204).
+ *   - Unless a parameter is named dev_*, buffers are HOST memory allocated by the caller; the
+ *     library performs the host<->device copies on the handle's stream and synchronises it.
+ *   - Arrays are per game, game-major: out[g][...] for g in [0, n_games).
+ *   - Tiles are row*20+col (0..399); players/seats are 0..3; piece ids are the PIECE_TYPES order of
+ *     blokus/src/pieces.rs:30-52.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with BK_ERR_CUDA.
+ */
+#ifndef BLOKUS_B200_H
+#define BLOKUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_BOARD_DIM 20
+#define BK_BOARD_TILES 400
+#define BK_NUM_PLAYERS 4
+#define BK_MAX_PLIES 360 /* >= 4 players * 89 squares */
+
+typedef enum bk_status {
+    BK_OK = 0,
+    BK_ERR_INVALID_ARG = -1,
+    BK_ERR_CUDA = -2,
+    BK_ERR_ILLEGAL_MOVE = -3, /* some game rejected its tile; see the per-game status output */
+    BK_ERR_CAPACITY = -4,     /* a per-game tree / output pool overflowed */
+    BK_ERR_STATE = -5         /* call not valid in the handle's current phase */
+} bk_status;
+
+typedef struct bk_env bk_env;           /* a batch of Game values (game.rs:91-99) in HBM */
+typedef struct bk_selfplay bk_selfplay; /* a batch of self-play clients (simulation.rs:267-296) */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* bk_last_error(void);
+const char* bk_version(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int bk_device_count(void);
+
+/* ---- static piece tables (blokus/src/pieces.rs:58-210) ------------------------------------------ */
+/* Piece::points (pieces.rs:153) */
+int bk_piece_points(int piece_id);
+/* Piece::variants.len() (pieces.rs:185-209) */
+int bk_piece_num_variants(int piece_id);
+/* PieceVariant{offsets,width} and variant.len() (pieces.rs:66-98). offsets_out holds <= 5 ints.
+ * Returns the number of offsets, or a negative status. */
+int bk_piece_variant(int piece_id, int variant, int* width_out, int* len_out, int* offsets_out);
+
+/* ---- game batch: Game (blokus/src/game.rs) -------------------------------------------------------- */
+/* Game::reset() for n_games games on `device` (game.rs:102-114). */
+int bk_env_create(int n_games, int device, bk_env** out);
+void bk_env_destroy(bk_env* env);
+int bk_env_num_games(const bk_env* env);
+/* Game::reset() in place for every game. */
+int bk_env_reset(bk_env* env);
+/* Game::clone() (game.rs:91 #[derive(Clone)]): a new batch with identical state on the same device. */
+int bk_env_clone(const bk_env* env, bk_env** out);
+
+/* Game::apply(tile, piece_to_finish) (game.rs:150-194) for every game at once.
+ *   tiles[g] < 0            : game g is skipped this call.
+ *   piece_to_finish         : NULL, or per game the index into the mover's REMAINING piece list
+ *                             (board.rs:151-153) to commit after this tile; < 0 means None.
+ *   status_out              : NULL, or per game 0 ok / BK_ERR_ILLEGAL_MOVE / 1 skipped.
+ * Deviation from the reference: an illegal tile is rejected WITHOUT mutating that
+ * game (the reference mutates the board and then returns Err, game.rs:152-164; no caller relies on
+ * that state).  Returns BK_ERR_ILLEGAL_MOVE if any game rejected its tile. */
+int bk_env_apply(bk_env* env, const int32_t* tiles, const int32_t* piece_to_finish, int32_t* status_out);
+
+/* Game::place_piece(p, v, o) (game.rs:116-144), in place (the reference returns a new Game; use
+ * bk_env_clone first for value semantics).  p = index into the mover's remaining list, v = variant
+ * index within the piece, o = stride-20 offset of the variant's bounding box.  p[g] < 0 skips game g.
+ * Only valid at the start of a turn (which is how gui/src/app.rs:156 uses it). */
+int bk_env_place_piece(bk_env* env, const int32_t* p, const int32_t* v, const int32_t* o, int32_t* status_out);
+
+/* Game::get_legal_tiles() (game.rs:242-244) as a 0/1 mask per tile, out[g][400]. Mid-piece this is
+ * the narrowed set, as in the reference. */
+int bk_env_legal_mask(bk_env* env, uint8_t* out);
+/* Same set as 20 row words per game (bit c of out[g][r] = tile r*20+c). */
+int bk_env_legal_rows(bk_env* env, uint32_t* out);
+/* Game::get_board() (game.rs:196-198): the reference's byte encoding, out[g][400]: occupied cell =
+ * 0xF0 | owner(1..4); empty cell = OR of 1<<(4+p) over players p with an orthogonal neighbour
+ * (board.rs:95-119). */
+int bk_env_board(bk_env* env, uint8_t* out);
+/* Board::get_anchors(player) (board.rs:143-145) as a 0/1 mask, out[g][400]; player < 0 = the
+ * current player (Game::get_current_anchors, game.rs:238-240). */
+int bk_env_anchors(bk_env* env, int player, uint8_t* out);
+/* Game::current_player() (game.rs:225-228), out[g]. */
+int bk_env_current_player(bk_env* env, int32_t* out);
+/* Game::is_terminal() (game.rs:275-277), out[g] 0/1. */
+int bk_env_is_terminal(bk_env* env, int32_t* out);
+/* Game::is_player_active(p) (game.rs:279-281), out[g][4] 0/1. */
+int bk_env_is_player_active(bk_env* env, int32_t* out);
+/* Game::get_score() (game.rs:247-249; board.rs:155-181), out[g][4]. */
+int bk_env_scores(bk_env* env, int32_t* out);
+/* Game::get_payoff() (game.rs:252-272), out[g][4]. */
+int bk_env_payoff(bk_env* env, float* out);
+/* Game::get_board_state() (game.rs:283-311): 5 planes 20x20, mover-relative and rotated to the
+ * mover's frame, out[g][5][20][20] as 0/1 bytes. */
+int bk_env_board_state(bk_env* env, uint8_t* out);
+/* Same planes written as float32 into DEVICE memory (the evaluator's input batch, replacing the
+ * nested-list pickle of simulation.rs:50-52 / model/training.py:29-40). */
+int bk_env_board_state_dev_f32(bk_env* env, float* dev_out);
+/* Game::history (game.rs:94): counts_out[g] plies, players_out/tiles_out[g][BK_MAX_PLIES]. */
+int bk_env_history(bk_env* env, int32_t* counts_out, int32_t* players_out, int32_t* tiles_out);
+/* Remaining pieces per player as piece-id bit masks, out[g][4] (Board::get_pieces, board.rs:147;
+ * the remaining LIST is the set bits in ascending id order). */
+int bk_env_pieces(bk_env* env, uint32_t* out);
+/* last_piece_lens (game.rs:98), out[g][4]. */
+int bk_env_last_piece_lens(bk_env* env, int32_t* out);
+/* Order-independent 64-bit digest of each game's full state (tests/trace hashes), out[g]. */
+int bk_env_digest(bk_env* env, uint64_t* out);
+
+/* ---- lockstep random playouts (BASELINE.json configs 1-2) --------------------------------------- */
+#define BK_PLAYOUT_HASH 1u     /* also fold a per-ply state digest into hash_out (parity runs) */
+#define BK_PLAYOUT_MIN_TILE 2u /* policy: always the smallest legal tile (seed-free trace)     */
+#define BK_PLAYOUT_MAX_TILE 4u /* policy: always the largest legal tile  (seed-free trace)     */
+/* Plays every game of the batch forward from its current state until it is terminal or max_plies
+ * more tiles were applied (max_plies < 0: to the end), entirely on the device: legal-tile
+ * generation, seeded choice, Game::apply, per ply.  Default policy: ascending legal tiles, index
+ * floor(u*n) with u from Philox4x32-10 keyed (seed, first_game_id+g, ply).
+ * The env keeps the final states; query them with the bk_env_* calls. */
+int bk_env_playout(bk_env* env, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags);
+/* Results of the last bk_env_playout: per game steps applied by it, and the chained trace hash
+ * (0 unless BK_PLAYOUT_HASH).  Either pointer may be NULL. */
+int bk_env_playout_results(bk_env* env, int32_t* steps_out, uint64_t* hash_out);
+/* Device time of the kernels launched by the last bk_env_playout / bk_env_apply, CUDA events on the
+ * handle's stream. */
+int bk_env_last_kernel_ms(bk_env* env, float* ms_out);
+/* Work counters of the last bk_env_playout summed over the batch: [0] steps, [1] turn-start move
+ * generations, [2] sum of 120*C_rem over those generations (SURVEY.md §8d algorithmic lane-ops). */
+int bk_env_playout_counters(bk_env* env, uint64_t out[3]);
+
+/* ---- MCTS self-play clients (self_play/src/simulation.rs) ------------------------------------------ */
+/* simulation.rs:14-22 plus the seed the reference lacks. */
+typedef struct bk_config {
+    uint32_t sims_per_move;
+    uint32_t sample_moves;
+    float c_base;
+    float c_init;
+    float dirichlet_alpha;
+    float exploration_fraction;
+    uint64_t seed;
+} bk_config;
+
+/* n_games clients with global ids first_game_id.. (RNG keyed by global id, so results do not depend
+ * on how games are sharded over GPUs).  max_children_per_game bounds the per-ply child pool
+ * (0 = worst case (sims_per_move+1)*126). */
+int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t first_game_id,
+                       uint32_t max_children_per_game, bk_selfplay** out);
+void bk_selfplay_destroy(bk_selfplay* sp);
+/* training_game() with the fixed-prior stub evaluator (policy 1.0 on legal tiles, value 0.25 per
+ * seat; BASELINE.json config 3) for up to max_plies more plies per game (< 0: to the end), fully on
+ * the device: per ply mcts() = root evaluate, Dirichlet noise, sims_per_move x (select, apply,
+ * evaluate/expand, backpropagate), policy record, select_action, Game::apply. */
+int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies);
+/* External-evaluator protocol, one leaf per live game per round (replaces queue.put / pipe.recv of
+ * simulation.rs:50-57 by one contiguous device batch):
+ *   bk_selfplay_begin_ply     : start mcts() for every live game; leaf = root.
+ *   bk_selfplay_leaf_planes   : dev_planes[n_games][5][20][20] float32 of each game's pending leaf
+ *                               (zeros for games with none); live_out (host, may be NULL) = number
+ *                               of games with a pending leaf.
+ *   bk_selfplay_expand_backup : consume dev_policy[n_games][400] (mover frame) and
+ *                               dev_value[n_games][4] (relative seat), expand + backpropagate, then
+ *                               run selection for the next simulation (terminal leaves are backed up
+ *                               on the device without an evaluator round).
+ *   bk_selfplay_end_ply       : record the policy, select_action, Game::apply.
+ * sims_done_out: simulations completed in the current ply (same for every live game). */
+int bk_selfplay_begin_ply(bk_selfplay* sp);
+int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* live_out);
+int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* sims_done_out);
+int bk_selfplay_end_ply(bk_selfplay* sp);
+/* Number of games not yet terminal. */
+int bk_selfplay_live_games(bk_selfplay* sp, int32_t* out);
+/* The batch of games being played (borrowed; valid until bk_selfplay_destroy). */
+bk_env* bk_selfplay_env(bk_selfplay* sp);
+/* training_game()'s return value (simulation.rs:293-295) for every game:
+ *   plies_out[g]; history via bk_env_history on bk_selfplay_env();
+ *   policy records: policy_off_out[g][BK_MAX_PLIES+1] offsets into that game's slice of
+ *   policy_tile_out / policy_visits_out (each [g][policy_cap]); prob = visits / sum(visits) in f32
+ *   (simulation.rs:213-225).  payoff via bk_env_payoff.  Returns BK_ERR_CAPACITY if policy_cap is
+ *   too small. */
+int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off_out, int32_t policy_cap,
+                        int16_t* policy_tile_out, uint32_t* policy_visits_out);
+/* Root children of the LAST searched ply of each game (debug / Q parity): counts_out[g], then
+ * [g][400] tile, visits, value_sum, prior. */
+int bk_selfplay_last_root(bk_selfplay* sp, int32_t* counts_out, int16_t* tile_out, uint32_t* visits_out,
+                          float* value_sum_out, float* prior_out);
+/* Counters since creation: [0] simulations, [1] Game::apply calls, [2] turn-start move generations,
+ * [3] sum of 120*C_rem, [4] child entries created, [5] nodes expanded. */
+int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]);
+int bk_selfplay_last_kernel_ms(bk_selfplay* sp, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOKUS_B200_H */
