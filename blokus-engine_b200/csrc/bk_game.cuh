@@ -142,7 +142,7 @@ __device__ __forceinline__ void bk_free_anchor(uint32_t mine, uint32_t occ, int 
 
 // Turn-start legal-tile board of a player: union of the cells of every valid placement of every
 // remaining piece (get_tile_moves keys, game.rs:60-74).  Fully unrolled over the 91 variants.
-__device__ __noinline__ uint32_t bk_movegen_rows(uint32_t bk_free, uint32_t bk_anch, uint32_t bk_pieces, int lane) {
+static __device__ __noinline__ uint32_t bk_movegen_rows(uint32_t bk_free, uint32_t bk_anch, uint32_t bk_pieces, int lane) {
 #include "bk_movegen_gen.inc"
     return bk_legal & BK_ROWMASK;
 }

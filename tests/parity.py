@@ -1,0 +1,195 @@
+"""Parity checks shared by the CPU-emulator tests and the GPU tests: the same assertions run against
+whichever build of the kernel sources `lib` is."""
+import numpy as np
+
+from blokus_self_play import GameBatch, PLAYOUT_HASH, PLAYOUT_MIN_TILE, PLAYOUT_MAX_TILE, BkError
+
+
+def oracle_mask(tiles):
+    m = np.zeros(400, dtype=np.uint8)
+    m[list(tiles)] = 1
+    return m
+
+
+def compare_state(batch, games, what="all"):
+    """Every accessor of the batch against the oracle games (bit-exact)."""
+    n = batch.n
+    lm = batch.legal_mask()
+    cur = batch.current_player()
+    term = batch.is_terminal()
+    for g in range(n):
+        assert np.array_equal(lm[g], oracle_mask(games[g].legal_tiles())), f"legal tiles differ, game {g}"
+        assert term[g] == games[g].is_terminal()
+        assert cur[g] == games[g].current_player(), f"current player differs, game {g}"
+    if what != "all":
+        return
+    board = batch.board()
+    planes = batch.board_state()
+    act = batch.is_player_active()
+    sc = batch.scores()
+    pay = batch.payoff()
+    pcs = batch.pieces()
+    ll = batch.last_piece_lens()
+    dg = batch.digest()
+    anch = [batch.anchors(p) for p in range(4)]
+    anch_cur = batch.anchors(-1)
+    hist = batch.history()
+    for g in range(n):
+        og = games[g]
+        assert np.array_equal(board[g], og.board()), f"board bytes differ, game {g}"
+        assert np.array_equal(planes[g], og.board_state()), f"planes differ, game {g}"
+        assert act[g].tolist() == [og.is_player_active(p) for p in range(4)]
+        assert sc[g].tolist() == og.scores()
+        assert pay[g].tolist() == og.payoff()
+        assert ll[g].tolist() == og.last_piece_lens()
+        for p in range(4):
+            mask = 0
+            for pid in og.pieces(p):
+                mask |= 1 << pid
+            assert int(pcs[g, p]) == mask
+            assert np.array_equal(anch[p][g], oracle_mask(og.anchors(p))), f"anchors differ, game {g} player {p}"
+        assert np.array_equal(anch_cur[g], oracle_mask(og.anchors(-1)))
+        assert int(dg[g]) == og.digest()
+        assert hist[g] == og.history()
+
+
+def check_stepwise(lib, orc, n_games=4, seed=0, max_plies=10**9, full_every=1):
+    """Lockstep random games through Game::apply on both sides, comparing after every ply."""
+    rng = np.random.default_rng(seed)
+    batch = GameBatch(n_games, lib=lib)
+    games = [orc.Game() for _ in range(n_games)]
+    compare_state(batch, games)
+    ply = 0
+    while ply < max_plies and not all(g.is_terminal() for g in games):
+        tiles = []
+        for g in games:
+            if g.is_terminal():
+                tiles.append(-1)
+            else:
+                lt = g.legal_tiles()
+                tiles.append(int(lt[rng.integers(len(lt))]))
+        st = batch.apply(tiles)
+        for i, g in enumerate(games):
+            if tiles[i] >= 0:
+                assert st[i] == 0
+                assert g.apply(tiles[i])
+            else:
+                assert st[i] == 1
+        ply += 1
+        compare_state(batch, games, "all" if ply % full_every == 0 else "light")
+    compare_state(batch, games)
+    batch.close()
+    return ply
+
+
+def check_playout(lib, orc, n_games, seed, first_game_id=0, n_check=None, flags=0):
+    """Device-resident playout to the end vs the oracle's trace (hash of every ply's full state)."""
+    batch = GameBatch(n_games, lib=lib)
+    res = batch.playout(seed=seed, first_game_id=first_game_id, flags=flags | PLAYOUT_HASH)
+    assert batch.is_terminal().all()
+    scores = batch.scores()
+    hist = batch.history()
+    policy = 1 if flags & PLAYOUT_MIN_TILE else (2 if flags & PLAYOUT_MAX_TILE else 0)
+    idx = range(n_games) if n_check is None else np.linspace(0, n_games - 1, n_check).astype(int)
+    for g in idx:
+        ref = orc.playout(seed, first_game_id + int(g), policy)
+        assert ref["n_plies"] == int(res["steps"][g])
+        assert ref["hash"] == int(res["hash"][g]), f"trace hash differs, game {g}"
+        assert list(ref["scores"]) == scores[g].tolist()
+        assert [t for _, t in hist[g]] == ref["tiles"].tolist()
+        assert [p for p, _ in hist[g]] == ref["players"].tolist()
+    assert int(res["total_steps"]) == int(np.sum(res["steps"]))
+    batch.close()
+    return res
+
+
+def check_illegal_move(lib, orc):
+    """An illegal tile is rejected with an error and the game is left untouched."""
+    batch = GameBatch(3, lib=lib)
+    before = batch.digest().copy()
+    st = batch.apply([399, 0, 5], strict=False)  # 399 and 5 are not legal for player 0 at the start
+    assert st.tolist() == [-3, 0, -3]
+    after = batch.digest()
+    assert after[0] == before[0] and after[2] == before[2] and after[1] != before[1]
+    try:
+        batch.apply([399, -1, -1])
+        raised = False
+    except BkError as e:
+        raised = e.code == -3 and "Invalid move" in str(e)
+    assert raised
+    batch.close()
+
+
+def check_place_piece(lib, orc, seed=0, n_turns=40):
+    """Game::place_piece against the oracle: random (p, v, o) proposals, legal and illegal."""
+    rng = np.random.default_rng(seed)
+    batch = GameBatch(1, lib=lib)
+    og = orc.Game()
+    done_legal = 0
+    for _ in range(n_turns):
+        if og.is_terminal():
+            break
+        pieces = og.pieces(og.current_player())
+        # a few random proposals (mostly illegal), then a legal one built from the oracle's anchors
+        for _k in range(3):
+            p = int(rng.integers(0, len(pieces) + 1))
+            v = int(rng.integers(0, 9))
+            o = int(rng.integers(0, 400))
+            probe = og.clone()
+            rc = probe.place_piece(p, v, o)
+            st = batch.clone().place_piece([p], [v], [o], strict=False)
+            assert (st[0] == 0) == (rc == 0), (p, v, o, rc, st)
+        found = None
+        anchors = og.anchors(-1)
+        order = rng.permutation(len(pieces))
+        for p in order:
+            nv = orc.piece_num_variants(pieces[p])
+            for v in rng.permutation(nv):
+                var = orc.piece_variant(pieces[p], int(v))
+                for a in anchors:
+                    for off in var["offsets"]:
+                        if off <= a:
+                            probe = og.clone()
+                            if probe.place_piece(int(p), int(v), a - off) == 0:
+                                found = (int(p), int(v), a - off)
+                                break
+                    if found:
+                        break
+                if found:
+                    break
+            if found:
+                break
+        assert found is not None
+        assert og.place_piece(*found) == 0
+        st = batch.place_piece([found[0]], [found[1]], [found[2]])
+        assert st[0] == 0
+        compare_state(batch, [og])
+        done_legal += 1
+    batch.close()
+    return done_legal
+
+
+def check_piece_to_finish(lib, orc, seed=0, n_steps=60):
+    """Game::apply(tile, Some(p)) (game.rs:176-187): the reference commits remaining-list entry p
+    blindly after this tile; random mixes of None / Some(p) must track the oracle exactly."""
+    rng = np.random.default_rng(seed)
+    batch = GameBatch(1, lib=lib)
+    og = orc.Game()
+    for _ in range(n_steps):
+        if og.is_terminal():
+            break
+        pieces = og.pieces(og.current_player())
+        lt = og.legal_tiles()
+        tile = int(lt[rng.integers(len(lt))])
+        fin = int(rng.integers(len(pieces))) if rng.random() < 0.3 else None
+        assert og.apply(tile, fin)
+        st = batch.apply([tile], None if fin is None else [fin])
+        assert st[0] == 0
+        compare_state(batch, [og])
+    # out-of-range piece index: rejected, game untouched (the reference would panic in Vec::remove)
+    if not og.is_terminal():
+        before = batch.digest()[0]
+        lt = og.legal_tiles()
+        st = batch.apply([lt[0]], [21], strict=False)
+        assert st[0] == -3 and batch.digest()[0] == before
+    batch.close()

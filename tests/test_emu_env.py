@@ -1,0 +1,37 @@
+"""Kernel-source logic checks on the CPU warp emulator (tests/warp_emu): the same parity assertions the
+GPU tests make, at sizes the emulator finishes in seconds.  These prove the SOURCE is right before any
+GPU minute is spent; the GPU tests (test_gpu_env.py) prove the sm_100a BUILD is."""
+import parity
+
+
+def test_emu_stepwise_full_state(emu_lib, orc):
+    plies = parity.check_stepwise(emu_lib, orc, n_games=2, seed=11, max_plies=60, full_every=1)
+    assert plies == 60
+
+
+def test_emu_stepwise_to_terminal(emu_lib, orc):
+    plies = parity.check_stepwise(emu_lib, orc, n_games=3, seed=5, full_every=25)
+    assert plies > 240
+
+
+def test_emu_playout_traces(emu_lib, orc):
+    parity.check_playout(emu_lib, orc, n_games=4, seed=99, first_game_id=1000)
+
+
+def test_emu_seed_free_traces(emu_lib, orc):
+    r = parity.check_playout(emu_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MIN_TILE)
+    assert int(r["steps"][0]) == 314
+    r = parity.check_playout(emu_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MAX_TILE)
+    assert int(r["steps"][0]) == 314
+
+
+def test_emu_illegal_move(emu_lib, orc):
+    parity.check_illegal_move(emu_lib, orc)
+
+
+def test_emu_place_piece(emu_lib, orc):
+    assert parity.check_place_piece(emu_lib, orc, seed=3, n_turns=12) == 12
+
+
+def test_emu_piece_to_finish(emu_lib, orc):
+    parity.check_piece_to_finish(emu_lib, orc, seed=4, n_steps=40)

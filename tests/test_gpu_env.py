@@ -1,0 +1,96 @@
+"""Parity tests proper: the sm_100a build, through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_stepwise_full_state(cuda_lib, orc):
+    plies = parity.check_stepwise(cuda_lib, orc, n_games=16, seed=21, full_every=1)
+    assert plies > 240
+
+
+def test_gpu_playout_traces_config1(cuda_lib, orc):
+    """BASELINE.json config 1: single game, seeded random legal moves, bit-exact trace."""
+    for seed in (0, 1, 2):
+        parity.check_playout(cuda_lib, orc, n_games=1, seed=seed)
+
+
+def test_gpu_seed_free_traces(cuda_lib, orc):
+    r = parity.check_playout(cuda_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MIN_TILE)
+    assert int(r["steps"][0]) == 314
+    r = parity.check_playout(cuda_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MAX_TILE)
+    assert int(r["steps"][0]) == 314
+
+
+def test_gpu_playout_4096_config2(cuda_lib, orc):
+    """BASELINE.json config 2 at full size: 4096 lockstep games; 256 of them checked against the oracle
+    ply by ply (trace hash), all of them through size-independent invariants."""
+    from blokus_self_play import GameBatch
+    res = parity.check_playout(cuda_lib, orc, n_games=4096, seed=777, n_check=256)
+    assert res["steps"].min() >= 200 and res["steps"].max() <= 356
+    b = GameBatch(4096, lib=cuda_lib)
+    r2 = b.playout(seed=777, flags=parity.PLAYOUT_HASH)
+    assert np.array_equal(r2["hash"], res["hash"])          # deterministic
+    board = b.board()
+    owners = board & 0x0F
+    sc = b.scores()
+    pcs = b.pieces()
+    ll = b.last_piece_lens()
+    for p in range(4):
+        tiles = (owners == p + 1).sum(axis=1)
+        bonus = np.where(pcs[:, p] == 0, 15 + 5 * (ll[:, p] == 1), 0)
+        assert np.array_equal(sc[:, p], tiles - 89 + bonus)
+    hist = b.history()
+    assert [len(h) for h in hist] == r2["steps"].tolist()
+    assert not b.legal_mask().any()                            # terminal: no legal tile anywhere
+    pay = b.payoff()
+    assert np.allclose(pay.sum(axis=1), 1.0)
+
+
+def test_gpu_sharding_invariance(cuda_lib, orc):
+    """Games are keyed by GLOBAL id: a shard starting at id 2048 equals the tail of the full batch."""
+    from blokus_self_play import GameBatch
+    a = GameBatch(512, lib=cuda_lib)
+    ra = a.playout(seed=5, first_game_id=0, flags=parity.PLAYOUT_HASH)
+    b = GameBatch(256, lib=cuda_lib)
+    rb = b.playout(seed=5, first_game_id=256, flags=parity.PLAYOUT_HASH)
+    assert np.array_equal(ra["hash"][256:], rb["hash"])
+
+
+def test_gpu_illegal_move(cuda_lib, orc):
+    parity.check_illegal_move(cuda_lib, orc)
+
+
+def test_gpu_place_piece(cuda_lib, orc):
+    assert parity.check_place_piece(cuda_lib, orc, seed=8, n_turns=70) >= 50
+
+
+def test_gpu_piece_to_finish(cuda_lib, orc):
+    for seed in range(4):
+        parity.check_piece_to_finish(cuda_lib, orc, seed=seed, n_steps=120)
+
+
+def test_gpu_clone_is_independent(cuda_lib, orc):
+    from blokus_self_play import GameBatch
+    a = GameBatch(8, lib=cuda_lib)
+    a.playout(seed=1, max_plies=50)
+    c = a.clone()
+    assert np.array_equal(a.digest(), c.digest())
+    c.playout(seed=2, max_plies=10)
+    assert not np.array_equal(a.digest(), c.digest())
+    a2 = a.clone()
+    assert np.array_equal(a.digest(), a2.digest()) and a.history() == a2.history()
+
+
+def test_gpu_max_plies_prefix(cuda_lib, orc):
+    """Stopping after k plies and resuming gives the same games as one uninterrupted run."""
+    from blokus_self_play import GameBatch
+    a = GameBatch(64, lib=cuda_lib)
+    a.playout(seed=9, max_plies=100)
+    a.playout(seed=9)
+    b = GameBatch(64, lib=cuda_lib)
+    b.playout(seed=9)
+    assert np.array_equal(a.digest(), b.digest()) and a.history() == b.history()
