@@ -5,4 +5,4 @@ include/blokus_b200.h.  Hand-written sm_100a kernels do all the work; there is n
 from ._lib import (BkConfig, BkError, Lib, default_lib, DEFAULT_LIB, MAX_PLIES,  # noqa: F401
                    PLAYOUT_HASH, PLAYOUT_MIN_TILE, PLAYOUT_MAX_TILE,
                    ERR_ILLEGAL_MOVE, ERR_CUDA, ERR_INVALID_ARG, ERR_CAPACITY, ERR_STATE)
-from .game import Game, GameBatch  # noqa: F401
+from .game import Game, GameBatch, probe_int_peak  # noqa: F401

@@ -81,8 +81,13 @@ _SIGNATURES = {
     "bk_env_last_piece_lens": (C.c_int, [_P, _P]),
     "bk_env_digest": (C.c_int, [_P, _P]),
     "bk_env_playout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32]),
+    "bk_env_playout_ids": (C.c_int, [_P, C.c_uint64, _P, C.c_int, C.c_uint32]),
+    "bk_env_fetch": (C.c_int, [_P, _P, _P, _P]),
+    "bk_probe_int_peak": (C.c_int, [C.c_int, _P, _P]),
     "bk_env_playout_results": (C.c_int, [_P, _P, _P]),
     "bk_env_last_kernel_ms": (C.c_int, [_P, _P]),
+    "bk_env_event_record": (C.c_int, [_P, C.c_int]),
+    "bk_env_event_elapsed": (C.c_int, [_P, _P]),
     "bk_env_playout_counters": (C.c_int, [_P, _P]),
     "bk_selfplay_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(BkConfig), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "bk_selfplay_destroy": (None, [_P]),

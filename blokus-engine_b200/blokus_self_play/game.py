@@ -136,9 +136,15 @@ class GameBatch:
         return [list(zip(pl[g, : cnt[g]].tolist(), tl[g, : cnt[g]].tolist())) for g in range(self.n)]
 
     # ---- lockstep random playouts (BASELINE.json configs 1-2) -------------------------------------
-    def playout(self, seed: int = 0, first_game_id: int = 0, max_plies: int = -1, flags: int = 0) -> dict:
-        """Play every game forward on the device (legal-move gen + seeded choice + apply per ply)."""
-        self.lib.check(self.lib.bk_env_playout(self._h, seed, first_game_id, max_plies, flags))
+    def playout(self, seed: int = 0, first_game_id: int = 0, max_plies: int = -1, flags: int = 0,
+                game_ids: Optional[np.ndarray] = None) -> dict:
+        """Play every game forward on the device (legal-move gen + seeded choice + apply per ply).
+        game_ids (uint32[n], host) gives each game its global id; default first_game_id + g."""
+        if game_ids is not None:
+            ids = np.ascontiguousarray(np.asarray(game_ids, dtype=np.uint32).reshape(self.n))
+            self.lib.check(self.lib.bk_env_playout_ids(self._h, seed, _ptr(ids), max_plies, flags))
+        else:
+            self.lib.check(self.lib.bk_env_playout(self._h, seed, first_game_id, max_plies, flags))
         steps = np.zeros(self.n, dtype=np.int32)
         hashes = np.zeros(self.n, dtype=np.uint64)
         self.lib.check(self.lib.bk_env_playout_results(self._h, _ptr(steps), _ptr(hashes)))
@@ -148,6 +154,50 @@ class GameBatch:
         self.lib.check(self.lib.bk_env_playout_counters(self._h, _ptr(ctr)))
         return {"steps": steps, "hash": hashes, "kernel_ms": ms.value, "total_steps": int(ctr[0]),
                 "movegens": int(ctr[1]), "lane_ops": int(ctr[2])}
+
+
+    def run_playout_raw(self, seed: int, ids_ptr, max_plies: int = -1, flags: int = 0) -> None:
+        """bk_env_playout_ids with a caller-held (pinned) uint32 id buffer; no result copies."""
+        self.lib.check(self.lib.bk_env_playout_ids(self._h, seed, ids_ptr, max_plies, flags))
+
+    def fetch_raw(self, plies_ptr, scores_ptr, hist_ptr) -> None:
+        """bk_env_fetch straight into caller-held (pinned) buffers."""
+        self.lib.check(self.lib.bk_env_fetch(self._h, plies_ptr, scores_ptr, hist_ptr))
+
+    def fetch(self):
+        """Finished-batch gather: plies[n], scores[n,4], packed history uint16[n,360] (tile | player<<9)."""
+        plies = np.zeros(self.n, dtype=np.int32)
+        scores = np.zeros((self.n, 4), dtype=np.int32)
+        hist = np.zeros((self.n, _lib.MAX_PLIES), dtype=np.uint16)
+        self.fetch_raw(_ptr(plies), _ptr(scores), _ptr(hist))
+        return plies, scores, hist
+
+    def event_record(self, which: int) -> None:
+        self.lib.check(self.lib.bk_env_event_record(self._h, which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        self.lib.check(self.lib.bk_env_event_elapsed(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        self.lib.check(self.lib.bk_env_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        ctr = np.zeros(3, dtype=np.uint64)
+        self.lib.check(self.lib.bk_env_playout_counters(self._h, _ptr(ctr)))
+        return {"total_steps": int(ctr[0]), "movegens": int(ctr[1]), "lane_ops": int(ctr[2])}
+
+
+def probe_int_peak(device: int = 0, lib: Optional[Lib] = None) -> float:
+    """Measured integer-pipe peak of the device, 32-bit lane-ops per second."""
+    lib = lib or _lib.default_lib()
+    v = C.c_double(0)
+    ms = C.c_float(0)
+    lib.check(lib.bk_probe_int_peak(device, C.byref(v), C.byref(ms)))
+    return v.value
 
 
 class Game:
@@ -208,4 +258,4 @@ class Game:
         return self._b.history()[0]
 
 
-__all__ = ["GameBatch", "Game", "BkError"]
+__all__ = ["GameBatch", "Game", "BkError", "probe_int_peak"]

@@ -47,7 +47,7 @@ k_place_piece(BkState* __restrict__ states, uint16_t* __restrict__ hist, const i
 // One warp per CTA: the hardware CTA scheduler balances games of different length over the SMs.
 __global__ void __launch_bounds__(32)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
-          int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
+          const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
           unsigned long long* counters) {
     __shared__ uint32_t smem[BK_TABS_SMEM_WORDS];
     const BkTabs tabs = bk_stage_tables(smem);
@@ -55,7 +55,32 @@ k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n) return;
-    kb_playout(states, hist, seed, first_id, max_plies, flags, steps_out, hash_out, counters, g, lane, tabs);
+    kb_playout(states, hist, seed, ids ? ids[g] : first_id + uint32_t(g), max_plies, flags, steps_out, hash_out, counters, g, lane, tabs);
+}
+
+__global__ void k_scores(const BkState* __restrict__ states, int32_t* __restrict__ plies, int32_t* __restrict__ scores, int n) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    kb_scores(states, plies, scores, g, lane);
+}
+
+// Integer-pipe peak probe: 8 independent LOP3/SHF chains per thread, exact op count by inline PTX.
+#define BK_PROBE_ITERS 4096
+__global__ void __launch_bounds__(256) k_int_probe(uint32_t* __restrict__ out) {
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const uint32_t k = blockIdx.x | 0x55aa00ffu;
+#ifndef BK_WARP_EMU
+#pragma unroll 1
+    for (int i = 0; i < BK_PROBE_ITERS; ++i) {
+#define BK_PROBE_STEP(x) asm volatile("lop3.b32 %0, %0, %1, %0, 0x96; shr.u32 %0, %0, 1;" : "+r"(x) : "r"(k));
+        BK_PROBE_STEP(a0) BK_PROBE_STEP(a1) BK_PROBE_STEP(a2) BK_PROBE_STEP(a3)
+        BK_PROBE_STEP(a4) BK_PROBE_STEP(a5) BK_PROBE_STEP(a6) BK_PROBE_STEP(a7)
+        BK_PROBE_STEP(a0) BK_PROBE_STEP(a1) BK_PROBE_STEP(a2) BK_PROBE_STEP(a3)
+        BK_PROBE_STEP(a4) BK_PROBE_STEP(a5) BK_PROBE_STEP(a6) BK_PROBE_STEP(a7)
+    }
+#endif
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ k;
 }
 
 __global__ void k_summary(const BkState* __restrict__ states, BkSummary* __restrict__ out, int n) {
@@ -111,6 +136,8 @@ int bk_env_alloc(int n_games, int device, cudaStream_t stream, bk_env** out) {
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventCreate(&e->ev0));
     BK_CUDA(cudaEventCreate(&e->ev1));
+    BK_CUDA(cudaEventCreate(&e->uev[0]));
+    BK_CUDA(cudaEventCreate(&e->uev[1]));
     *out = e;
     return BK_OK;
 }
@@ -201,6 +228,8 @@ void bk_env_destroy(bk_env* e) {
     cudaFree(e->d_counters); cudaFree(e->d_summary); cudaFree(e->d_bytes);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->uev[0]) cudaEventDestroy(e->uev[0]);
+    if (e->uev[1]) cudaEventDestroy(e->uev[1]);
     if (e->stream && !e->borrowed) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -363,14 +392,75 @@ int bk_env_history(bk_env* e, int32_t* counts_out, int32_t* players_out, int32_t
     return BK_OK;
 }
 
-int bk_env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags) {
+static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const uint32_t* ids_host, int max_plies,
+                       uint32_t flags) {
     int rc = env_use(e);
     if (rc) return rc;
+    uint32_t* d_ids = nullptr;
+    if (ids_host) {
+        d_ids = reinterpret_cast<uint32_t*>(e->d_i32 + size_t(e->n));
+        BK_CUDA(cudaMemcpyAsync(d_ids, ids_host, sizeof(uint32_t) * size_t(e->n), cudaMemcpyHostToDevice, e->stream));
+    }
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, max_plies, flags,
-                                          e->d_i32, e->d_hash, e->d_counters);
+    BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+              flags, e->d_i32, e->d_hash, e->d_counters);
     return env_finish_timed(e);
+}
+
+int bk_env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags) {
+    return env_playout(e, seed, first_game_id, nullptr, max_plies, flags);
+}
+
+int bk_env_playout_ids(bk_env* e, uint64_t seed, const uint32_t* game_ids, int max_plies, uint32_t flags) {
+    if (!game_ids) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_playout_ids: game_ids is null");
+    return env_playout(e, seed, 0u, game_ids, max_plies, flags);
+}
+
+int bk_env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out) {
+    int rc = env_use(e);
+    if (rc) return rc;
+    int32_t* d_plies = e->d_i32 + 2 * size_t(e->n);
+    int32_t* d_scores = reinterpret_cast<int32_t*>(e->d_bytes);
+    if (plies_out || scores_out) {
+        BK_LAUNCH(k_scores, grid_for(e->n, BK_STEP_WARPS), 32 * BK_STEP_WARPS, e->stream, e->d_states, d_plies, d_scores, e->n);
+        BK_CUDA(cudaGetLastError());
+    }
+    if (plies_out) BK_CUDA(cudaMemcpyAsync(plies_out, d_plies, sizeof(int32_t) * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+    if (scores_out) BK_CUDA(cudaMemcpyAsync(scores_out, d_scores, sizeof(int32_t) * 4 * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+    if (history_packed_out)
+        BK_CUDA(cudaMemcpyAsync(history_packed_out, e->d_hist, sizeof(uint16_t) * BK_HIST_CAP * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaStreamSynchronize(e->stream));
+    return BK_OK;
+}
+
+int bk_probe_int_peak(int device, double* lane_ops_per_s_out, float* ms_out) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return bk_fail(BK_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+    if (device < 0 || device >= count || !lane_ops_per_s_out) return bk_fail(BK_ERR_INVALID_ARG, "bk_probe_int_peak: bad argument");
+    BK_CUDA(cudaSetDevice(device));
+    const int grid = 148 * 8, block = 256;
+    uint32_t* d = nullptr;
+    BK_CUDA(cudaMalloc(&d, sizeof(uint32_t) * size_t(grid) * block));
+    cudaEvent_t a, b;
+    BK_CUDA(cudaEventCreate(&a));
+    BK_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        BK_CUDA(cudaEventRecord(a, nullptr));
+        BK_LAUNCH(k_int_probe, grid, block, nullptr, d);
+        BK_CUDA(cudaEventRecord(b, nullptr));
+        BK_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f;
+        BK_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    const double ops = double(grid) * block * double(BK_PROBE_ITERS) * 16.0 * 2.0;  // 16 steps x (lop3 + shr)
+    *lane_ops_per_s_out = ops / (double(best) * 1e-3);
+    if (ms_out) *ms_out = best;
+    return BK_OK;
 }
 
 int bk_env_playout_results(bk_env* e, int32_t* steps_out, uint64_t* hash_out) {
@@ -385,6 +475,23 @@ int bk_env_playout_results(bk_env* e, int32_t* steps_out, uint64_t* hash_out) {
 int bk_env_last_kernel_ms(bk_env* e, float* ms_out) {
     if (!e || !ms_out) return bk_fail(BK_ERR_INVALID_ARG, "null argument");
     *ms_out = e->last_ms;
+    return BK_OK;
+}
+
+int bk_env_event_record(bk_env* e, int which) {
+    int rc = env_use(e);
+    if (rc) return rc;
+    if (which < 0 || which > 1) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_event_record: which must be 0 or 1");
+    BK_CUDA(cudaEventRecord(e->uev[which], e->stream));
+    return BK_OK;
+}
+
+int bk_env_event_elapsed(bk_env* e, float* ms_out) {
+    int rc = env_use(e);
+    if (rc) return rc;
+    if (!ms_out) return bk_fail(BK_ERR_INVALID_ARG, "null argument");
+    BK_CUDA(cudaStreamSynchronize(e->stream));
+    BK_CUDA(cudaEventElapsedTime(ms_out, e->uev[0], e->uev[1]));
     return BK_OK;
 }
 

@@ -121,7 +121,7 @@ __device__ __forceinline__ void kb_place_piece(BkState* __restrict__ states, uin
 
 // Persistent lockstep playout: one warp plays its game to the end without leaving the SM.
 __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, uint64_t seed,
-                                           uint32_t first_id, int max_plies, uint32_t flags,
+                                           uint32_t game_id, int max_plies, uint32_t flags,
                                            int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
                                            unsigned long long* counters, int g, int lane, const BkTabs& tabs) {
     BkRegs G;
@@ -135,7 +135,7 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
         int idx;
         if (flags & BK_PLAYOUT_MIN_TILE_FLAG) idx = 0;
         else if (flags & BK_PLAYOUT_MAX_TILE_FLAG) idx = cnt - 1;
-        else idx = int(bk_playout_index(seed, first_id + uint32_t(g), G.ply, uint32_t(cnt)));
+        else idx = int(bk_playout_index(seed, game_id, G.ply, uint32_t(cnt)));
         const int tile = bk_legal_select(G.legal, idx, lane);
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;
@@ -150,6 +150,18 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     bk_store(&states[g], lane, G);
     if (lane == 0) { steps_out[g] = steps; hash_out[g] = h; }
     bk_flush_counters(ctr, uint32_t(steps), lane, counters);
+}
+
+__device__ __forceinline__ void kb_scores(const BkState* __restrict__ states, int32_t* __restrict__ plies,
+                                          int32_t* __restrict__ scores, int g, int lane) {
+    BkRegs G;
+    bk_load(&states[g], lane, G);
+    int sc[4];
+    bk_scores(G, sc);
+    if (lane == 0) {
+        plies[g] = int(G.ply);
+        for (int p = 0; p < 4; ++p) scores[g * 4 + p] = sc[p];
+    }
 }
 
 __device__ __forceinline__ void kb_summary(const BkState* __restrict__ states, BkSummary* __restrict__ out, int g,

@@ -38,6 +38,7 @@ struct bk_env {
     BkSummary* d_summary = nullptr;  // [n]
     uint8_t* d_bytes = nullptr;      // [n][2000] staging for masks / boards / planes
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t uev[2] = {nullptr, nullptr};  // caller-driven region timing
     float last_ms = 0.0f;
     bool borrowed = false;           // owned by a bk_selfplay
 };

@@ -133,15 +133,31 @@ int bk_env_digest(bk_env* env, uint64_t* out);
  * floor(u*n) with u from Philox4x32-10 keyed (seed, first_game_id+g, ply).
  * The env keeps the final states; query them with the bk_env_* calls. */
 int bk_env_playout(bk_env* env, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags);
+/* As bk_env_playout, but game g's global id is game_ids[g] (HOST array of n_games entries, copied to
+ * the device inside the call) — the form a sharded driver uses. */
+int bk_env_playout_ids(bk_env* env, uint64_t seed, const uint32_t* game_ids, int max_plies, uint32_t flags);
+/* One device->host gather of what a batch produced, straight into the caller's buffers on the handle's
+ * stream (pin them for full PCIe rate): plies_out[g] (history length), scores_out[g][4], and the history
+ * packed as uint16 (tile | player << 9), history_packed_out[g][BK_MAX_PLIES].  Pointers may be NULL. */
+int bk_env_fetch(bk_env* env, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out);
 /* Results of the last bk_env_playout: per game steps applied by it, and the chained trace hash
  * (0 unless BK_PLAYOUT_HASH).  Either pointer may be NULL. */
 int bk_env_playout_results(bk_env* env, int32_t* steps_out, uint64_t* hash_out);
 /* Device time of the kernels launched by the last bk_env_playout / bk_env_apply, CUDA events on the
  * handle's stream. */
 int bk_env_last_kernel_ms(bk_env* env, float* ms_out);
+/* Region timing on the handle's stream: record event `which` (0 = begin, 1 = end) now; elapsed is
+ * end - begin in ms after the stream has drained.  Lets a caller time several calls as one region with
+ * CUDA events on the stream the kernels are launched on. */
+int bk_env_event_record(bk_env* env, int which);
+int bk_env_event_elapsed(bk_env* env, float* ms_out);
 /* Work counters of the last bk_env_playout summed over the batch: [0] steps, [1] turn-start move
  * generations, [2] sum of 120*C_rem over those generations (SURVEY.md §8d algorithmic lane-ops). */
 int bk_env_playout_counters(bk_env* env, uint64_t out[3]);
+
+/* Measured integer-pipe peak of `device` in 32-bit lane-ops per second (LOP3/SHF mix, every SM busy):
+ * the denominator of the integer roofline the rules engine is bound by. */
+int bk_probe_int_peak(int device, double* lane_ops_per_s_out, float* ms_out);
 
 /* ---- MCTS self-play clients (self_play/src/simulation.rs) ------------------------------------------ */
 /* simulation.rs:14-22 plus the seed the reference lacks. */
