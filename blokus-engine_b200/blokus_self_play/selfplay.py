@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's self-play client (self_play/src/lib.rs:9-32,
+self_play/src/simulation.rs:267-296) over the C ABI: batches of MCTS self-play games on one B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import BkConfig, Lib
+from .game import GameBatch, _ptr
+
+
+class Config:
+    """The six attributes the reference's Rust side reads by name (simulation.rs:14-22; defaults are the
+    shipped model/training.py:267-272 values) plus `seed`, which the reference lacks."""
+
+    def __init__(self, sims_per_move=50, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.3,
+                 exploration_fraction=0.25, seed=0):
+        self.sims_per_move = sims_per_move
+        self.sample_moves = sample_moves
+        self.c_base = c_base
+        self.c_init = c_init
+        self.dirichlet_alpha = dirichlet_alpha
+        self.exploration_fraction = exploration_fraction
+        self.seed = seed
+
+
+def _to_bk_config(config) -> BkConfig:
+    """Reads the attributes by name, as `#[derive(FromPyObject)]` does (Python ints are fine for floats)."""
+    return BkConfig(int(config.sims_per_move), int(config.sample_moves), float(config.c_base), float(config.c_init),
+                    float(config.dirichlet_alpha), float(config.exploration_fraction), int(getattr(config, "seed", 0)))
+
+
+class SelfPlay:
+    """n self-play clients (bk_selfplay).  Game g has global id first_game_id + g."""
+
+    def __init__(self, n_games: int, config, first_game_id: int = 0, device: int = 0, lib: Optional[Lib] = None,
+                 max_children_per_game: int = 0):
+        self.lib = lib or _lib.default_lib()
+        self.lib.require_device()
+        self.n = int(n_games)
+        self.config = config
+        self.first_game_id = first_game_id
+        self._cfg = _to_bk_config(config)
+        h = C.c_void_p()
+        self.lib.check(self.lib.bk_selfplay_create(self.n, device, C.byref(self._cfg), first_game_id,
+                                                   max_children_per_game, C.byref(h)))
+        self._h = h
+        self.env = GameBatch(self.n, device=device, lib=self.lib, _handle=self.lib.bk_selfplay_env(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self.lib.bk_selfplay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_stub(self, max_plies: int = -1) -> float:
+        """training_game() with the fixed-prior stub evaluator, on the device; returns kernel ms."""
+        self.lib.check(self.lib.bk_selfplay_run_stub(self._h, max_plies))
+        return self.last_kernel_ms()
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        self.lib.check(self.lib.bk_selfplay_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def live_games(self) -> int:
+        v = C.c_int32(0)
+        self.lib.check(self.lib.bk_selfplay_live_games(self._h, C.byref(v)))
+        return v.value
+
+    def counters(self) -> dict:
+        c = np.zeros(6, dtype=np.uint64)
+        self.lib.check(self.lib.bk_selfplay_counters(self._h, _ptr(c)))
+        return {"sims": int(c[0]), "applies": int(c[1]), "movegens": int(c[2]), "lane_ops": int(c[3]),
+                "entries": int(c[4]), "nodes": int(c[5])}
+
+    def policy_records(self, policy_cap: int = 16384):
+        """Per game, per searched ply: (tiles int16[k], visits uint32[k]) of the root's children."""
+        plies = np.zeros(self.n, dtype=np.int32)
+        off = np.zeros((self.n, _lib.MAX_PLIES + 1), dtype=np.int32)
+        tiles = np.zeros((self.n, policy_cap), dtype=np.int16)
+        visits = np.zeros((self.n, policy_cap), dtype=np.uint32)
+        self.lib.check(self.lib.bk_selfplay_results(self._h, _ptr(plies), _ptr(off), policy_cap, _ptr(tiles), _ptr(visits)))
+        out = []
+        for g in range(self.n):
+            recs = []
+            for k in range(int(plies[g])):
+                a, b = int(off[g, k]), int(off[g, k + 1])
+                recs.append((tiles[g, a:b].copy(), visits[g, a:b].copy()))
+            out.append(recs)
+        return out
+
+    def last_root(self):
+        """Root children of the last searched ply: per game dict(tile, visits, value_sum, prior)."""
+        cnt = np.zeros(self.n, dtype=np.int32)
+        tile = np.zeros((self.n, 400), dtype=np.int16)
+        vis = np.zeros((self.n, 400), dtype=np.uint32)
+        w = np.zeros((self.n, 400), dtype=np.float32)
+        p = np.zeros((self.n, 400), dtype=np.float32)
+        self.lib.check(self.lib.bk_selfplay_last_root(self._h, _ptr(cnt), _ptr(tile), _ptr(vis), _ptr(w), _ptr(p)))
+        return [{"tile": tile[g, : cnt[g]].copy(), "visits": vis[g, : cnt[g]].copy(), "value_sum": w[g, : cnt[g]].copy(),
+                 "prior": p[g, : cnt[g]].copy()} for g in range(self.n)]
+
+    def game_data(self) -> List[Tuple[list, list, list]]:
+        """What training_game() returns for each game (simulation.rs:293-295):
+        (history [(player, tile)], policies [[(tile, prob)]], values [4])."""
+        hist = self.env.history()
+        pay = self.env.payoff()
+        recs = self.policy_records()
+        out = []
+        for g in range(self.n):
+            pols = []
+            for tiles, visits in recs[g]:
+                total = np.float32(visits.sum(dtype=np.uint32))
+                probs = visits.astype(np.float32) / total          # simulation.rs:222, f32 division
+                pols.append(list(zip(tiles.astype(int).tolist(), probs.tolist())))
+            out.append((hist[g][: len(pols)] if len(hist[g]) > len(pols) else hist[g], pols, pay[g].tolist()))
+        return out
+
+
+def play_training_games(ids: Sequence[int], config, device: int = 0, lib: Optional[Lib] = None):
+    """Batched form of play_training_game for the fixed-prior stub evaluator: ids must be consecutive
+    global game ids.  Returns [(history, policies, values)] in id order."""
+    ids = list(ids)
+    if not ids:
+        return []
+    if ids != list(range(ids[0], ids[0] + len(ids))):
+        raise ValueError("ids must be consecutive")
+    sp = SelfPlay(len(ids), config, first_game_id=ids[0], device=device, lib=lib)
+    try:
+        sp.run_stub(-1)
+        return sp.game_data()
+    finally:
+        sp.close()

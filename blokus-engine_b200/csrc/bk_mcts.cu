@@ -1,21 +1,300 @@
-// bk_mcts.cu — MCTS self-play clients (placeholder entry points; implementation in progress).
-#include "bk_host.h"
+// bk_mcts.cu — MCTS self-play clients: kernel wrappers and the bk_selfplay_* C ABI
+// (include/blokus_b200.h).  Host mirror of self_play/src/lib.rs:9-32 + simulation.rs:267-296, batched.
+#include <math.h>
+#include <stdio.h>
 
-struct bk_selfplay { int n; };
+#include <cmath>
+#include <vector>
+
+#include "bk_host.h"
+#include "bk_mcts_kernels.cuh"
+
+struct bk_selfplay {
+    int n = 0;
+    int device = 0;
+    bk_config cfg{};
+    uint32_t first_id = 0;
+    bk_env* env = nullptr;
+    BkSearchCfg dcfg{};
+    uint32_t* d_N = nullptr;
+    float* d_W = nullptr;
+    float* d_P = nullptr;
+    uint32_t* d_TN = nullptr;
+    BkState* d_nodes = nullptr;
+    double* d_scratch = nullptr;
+    BkSearchHdr* d_hdr = nullptr;
+    uint32_t* d_pol_off = nullptr;    // [n][BK_HIST_CAP + 1]
+    uint16_t* d_pol_tile = nullptr;   // [n][policy_cap]
+    uint32_t* d_pol_visits = nullptr; // [n][policy_cap]
+    float* d_ucb = nullptr;
+    float* d_prior = nullptr;
+    unsigned long long* d_counters = nullptr;  // [8], cumulative
+    uint8_t* d_stage = nullptr;       // [n][400 * 16] gather staging for last_root
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.0f;
+};
+
+// ---- kernels ------------------------------------------------------------------------------------------
+struct BkPools {
+    uint32_t* N; float* W; float* P; uint32_t* TN; BkState* nodes; double* scratch; BkSearchHdr* hdr;
+    uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
+};
+
+__device__ __forceinline__ BkTree bk_tree_of(const BkPools& pl, const BkSearchCfg& cfg, int g) {
+    BkTree t;
+    const size_t eo = size_t(g) * cfg.entry_cap;
+    t.N = pl.N + eo; t.W = pl.W + eo; t.P = pl.P + eo; t.TN = pl.TN + eo;
+    t.nodes = pl.nodes + size_t(g) * cfg.max_nodes;
+    t.scratch = pl.scratch + size_t(g) * 400;
+    return t;
+}
+
+__global__ void __launch_bounds__(32)
+k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies,
+                unsigned long long* counters) {
+    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ BkWarpSmem wsm;
+    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const BkTree tr = bk_tree_of(pl, cfg, g);
+    kb_selfplay_stub(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+                     pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies,
+                     counters, g, lane, tabs, wsm);
+}
+
+// gather the root's child block (tile, visits, value_sum, prior) of every game: out[g][400] x 4 arrays
+__global__ void k_last_root(BkSearchCfg cfg, BkPools pl, int n, int32_t* counts, int16_t* tile, uint32_t* visits,
+                            float* wsum, float* prior) {
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const BkTree tr = bk_tree_of(pl, cfg, g);
+    const bool have = pl.hdr[g].n_nodes > 0u;
+    const uint32_t off = have ? tr.nodes[0].pad[0] : 0u;
+    const int cnt = have ? int(tr.nodes[0].pad[1]) : 0;
+    if (threadIdx.x == 0) counts[g] = cnt;
+    for (int i = threadIdx.x; i < 400; i += blockDim.x) {
+        const bool in = i < cnt;
+        tile[size_t(g) * 400 + i] = in ? int16_t(tr.TN[off + i] & 0xFFFFu) : int16_t(-1);
+        visits[size_t(g) * 400 + i] = in ? tr.N[off + i] : 0u;
+        wsum[size_t(g) * 400 + i] = in ? tr.W[off + i] : 0.0f;
+        prior[size_t(g) * 400 + i] = in ? tr.P[off + i] : 0.0f;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static float host_exp_f32(float x) { return float(std::exp(double(x))); }  // same definition as bk_exp_f32
+
+static BkPools pools_of(const bk_selfplay* sp) {
+    BkPools p;
+    p.N = sp->d_N; p.W = sp->d_W; p.P = sp->d_P; p.TN = sp->d_TN; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
+    p.hdr = sp->d_hdr; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
+    return p;
+}
+
+static int sp_use(const bk_selfplay* sp) {
+    if (!sp) return bk_fail(BK_ERR_INVALID_ARG, "null bk_selfplay handle");
+    BK_CUDA(cudaSetDevice(sp->device));
+    return BK_OK;
+}
+
+static int sp_check_errors(bk_selfplay* sp) {
+    std::vector<BkSearchHdr> h(size_t(sp->n));
+    BK_CUDA(cudaMemcpy(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * h.size(), cudaMemcpyDeviceToHost));
+    for (int g = 0; g < sp->n; ++g) {
+        const uint32_t e = h[size_t(g)].err;
+        if (!e) continue;
+        char buf[160];
+        snprintf(buf, sizeof buf, "self-play game %d stopped: flags 0x%x (%s%s%s%s%s)", g, e,
+                 (e & BK_SP_ERR_ENTRY_CAP) ? "child/node pool full " : "", (e & BK_SP_ERR_PATH_CAP) ? "path too deep " : "",
+                 (e & BK_SP_ERR_NO_CHILD) ? "no selectable child " : "", (e & BK_SP_ERR_POLICY_CAP) ? "policy pool full " : "",
+                 (e & BK_SP_ERR_APPLY) ? "illegal tile " : "");
+        return bk_fail((e & (BK_SP_ERR_ENTRY_CAP | BK_SP_ERR_POLICY_CAP | BK_SP_ERR_PATH_CAP)) ? BK_ERR_CAPACITY : BK_ERR_STATE, buf);
+    }
+    return BK_OK;
+}
 
 extern "C" {
+
+int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t first_game_id,
+                       uint32_t max_children_per_game, bk_selfplay** out) {
+    if (!cfg || !out || n_games <= 0) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: bad argument");
+    if (cfg->sims_per_move == 0 || cfg->sims_per_move > 65000u)
+        return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: sims_per_move must be in 1..65000");
+    if (!(cfg->c_base > 0.0f)) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: c_base must be > 0");
+    if (!(cfg->dirichlet_alpha > 0.0f)) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: dirichlet_alpha must be > 0");
+    bk_selfplay* sp = new bk_selfplay();
+    sp->n = n_games;
+    sp->device = device;
+    sp->cfg = *cfg;
+    sp->first_id = first_game_id;
+    int rc = bk_env_create(n_games, device, &sp->env);
+    if (rc) { delete sp; return rc; }
+    BkSearchCfg& d = sp->dcfg;
+    d.sims = cfg->sims_per_move;
+    d.sample_moves = cfg->sample_moves;
+    d.frac = cfg->exploration_fraction;
+    d.alpha = cfg->dirichlet_alpha;
+    d.seed = cfg->seed;
+    d.first_game_id = first_game_id;
+    d.max_nodes = cfg->sims_per_move + 2u;
+    d.entry_cap = max_children_per_game ? max_children_per_game : (cfg->sims_per_move + 2u) * 128u;
+    d.policy_cap = 16384u;
+    d.stub_value = 0.25f;
+    const size_t ne = size_t(n_games) * d.entry_cap;
+    BK_CUDA(cudaMalloc(&sp->d_N, sizeof(uint32_t) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_W, sizeof(float) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_P, sizeof(float) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_TN, sizeof(uint32_t) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_nodes, sizeof(BkState) * size_t(n_games) * d.max_nodes));
+    BK_CUDA(cudaMalloc(&sp->d_scratch, sizeof(double) * 400 * size_t(n_games)));
+    BK_CUDA(cudaMalloc(&sp->d_hdr, sizeof(BkSearchHdr) * size_t(n_games)));
+    BK_CUDA(cudaMalloc(&sp->d_pol_off, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games)));
+    BK_CUDA(cudaMalloc(&sp->d_pol_tile, sizeof(uint16_t) * size_t(d.policy_cap) * size_t(n_games)));
+    BK_CUDA(cudaMalloc(&sp->d_pol_visits, sizeof(uint32_t) * size_t(d.policy_cap) * size_t(n_games)));
+    BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 8));
+    BK_CUDA(cudaMalloc(&sp->d_stage, size_t(n_games) * 400 * 16));
+    BK_CUDA(cudaMemset(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games)));
+    BK_CUDA(cudaMemset(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games)));
+    BK_CUDA(cudaMemset(sp->d_counters, 0, sizeof(unsigned long long) * 8));
+    // simulation.rs:91-93 — the factor of ucb_score that depends only on the parent's visit count,
+    // evaluated on the host with the platform libm exactly as the reference's f32 expression reads
+    std::vector<float> ucb(size_t(cfg->sims_per_move) + 2);
+    for (size_t i = 0; i < ucb.size(); ++i) {
+        const float pv = float(i);
+        ucb[i] = (std::log((pv + cfg->c_base + 1.0f) / cfg->c_base) + cfg->c_init) * std::sqrt(pv);
+    }
+    // simulation.rs:67-80 for the stub's constant policy 1.0: prior = e / (sequential f32 sum of n e's)
+    std::vector<float> prior(401, 0.0f);
+    const float e1 = host_exp_f32(1.0f);
+    float total = 0.0f;
+    for (int k = 1; k <= 400; ++k) { total += e1; prior[size_t(k)] = e1 / total; }
+    BK_CUDA(cudaMalloc(&sp->d_ucb, sizeof(float) * ucb.size()));
+    BK_CUDA(cudaMalloc(&sp->d_prior, sizeof(float) * prior.size()));
+    BK_CUDA(cudaMemcpy(sp->d_ucb, ucb.data(), sizeof(float) * ucb.size(), cudaMemcpyHostToDevice));
+    BK_CUDA(cudaMemcpy(sp->d_prior, prior.data(), sizeof(float) * prior.size(), cudaMemcpyHostToDevice));
+    d.ucb_tab = sp->d_ucb;
+    d.prior_tab = sp->d_prior;
+    BK_CUDA(cudaEventCreate(&sp->ev0));
+    BK_CUDA(cudaEventCreate(&sp->ev1));
+    *out = sp;
+    return BK_OK;
+}
+
+void bk_selfplay_destroy(bk_selfplay* sp) {
+    if (!sp) return;
+    cudaSetDevice(sp->device);
+    cudaFree(sp->d_N); cudaFree(sp->d_W); cudaFree(sp->d_P); cudaFree(sp->d_TN); cudaFree(sp->d_nodes);
+    cudaFree(sp->d_scratch); cudaFree(sp->d_hdr); cudaFree(sp->d_pol_off); cudaFree(sp->d_pol_tile);
+    cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
+    cudaFree(sp->d_stage);
+    if (sp->ev0) cudaEventDestroy(sp->ev0);
+    if (sp->ev1) cudaEventDestroy(sp->ev1);
+    bk_env_destroy(sp->env);
+    delete sp;
+}
+
+int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    cudaStream_t st = sp->env->stream;
+    BK_CUDA(cudaEventRecord(sp->ev0, st));
+    BK_LAUNCH(k_selfplay_stub, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+              max_plies, sp->d_counters);
+    BK_CUDA(cudaEventRecord(sp->ev1, st));
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(cudaEventElapsedTime(&sp->last_ms, sp->ev0, sp->ev1));
+    return sp_check_errors(sp);
+}
+
 #define BK_NOT_YET(name) return bk_fail(BK_ERR_STATE, name ": not implemented yet")
-int bk_selfplay_create(int, int, const bk_config*, uint32_t, uint32_t, bk_selfplay**) { BK_NOT_YET("bk_selfplay_create"); }
-void bk_selfplay_destroy(bk_selfplay*) {}
-int bk_selfplay_run_stub(bk_selfplay*, int) { BK_NOT_YET("bk_selfplay_run_stub"); }
 int bk_selfplay_begin_ply(bk_selfplay*) { BK_NOT_YET("bk_selfplay_begin_ply"); }
 int bk_selfplay_leaf_planes(bk_selfplay*, float*, int32_t*) { BK_NOT_YET("bk_selfplay_leaf_planes"); }
 int bk_selfplay_expand_backup(bk_selfplay*, const float*, const float*, int32_t*) { BK_NOT_YET("bk_selfplay_expand_backup"); }
 int bk_selfplay_end_ply(bk_selfplay*) { BK_NOT_YET("bk_selfplay_end_ply"); }
-int bk_selfplay_live_games(bk_selfplay*, int32_t*) { BK_NOT_YET("bk_selfplay_live_games"); }
-bk_env* bk_selfplay_env(bk_selfplay*) { return nullptr; }
-int bk_selfplay_results(bk_selfplay*, int32_t*, int32_t*, int32_t, int16_t*, uint32_t*) { BK_NOT_YET("bk_selfplay_results"); }
-int bk_selfplay_last_root(bk_selfplay*, int32_t*, int16_t*, uint32_t*, float*, float*) { BK_NOT_YET("bk_selfplay_last_root"); }
-int bk_selfplay_counters(bk_selfplay*, uint64_t*) { BK_NOT_YET("bk_selfplay_counters"); }
-int bk_selfplay_last_kernel_ms(bk_selfplay*, float*) { BK_NOT_YET("bk_selfplay_last_kernel_ms"); }
+
+int bk_selfplay_live_games(bk_selfplay* sp, int32_t* out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!out) return bk_fail(BK_ERR_INVALID_ARG, "null argument");
+    std::vector<int32_t> term(size_t(sp->n));
+    rc = bk_env_is_terminal(sp->env, term.data());
+    if (rc) return rc;
+    int live = 0;
+    for (int32_t t : term) live += t ? 0 : 1;
+    *out = live;
+    return BK_OK;
 }
+
+bk_env* bk_selfplay_env(bk_selfplay* sp) { return sp ? sp->env : nullptr; }
+
+int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off_out, int32_t policy_cap,
+                        int16_t* policy_tile_out, uint32_t* policy_visits_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    const size_t n = size_t(sp->n);
+    std::vector<BkSearchHdr> h(n);
+    BK_CUDA(cudaMemcpy(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> off(n * (BK_HIST_CAP + 1));
+    BK_CUDA(cudaMemcpy(off.data(), sp->d_pol_off, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost));
+    for (size_t g = 0; g < n; ++g) {
+        const uint32_t plies = h[g].plies_searched;
+        if (plies_out) plies_out[g] = int32_t(plies);
+        if (policy_off_out)
+            for (size_t k = 0; k <= BK_MAX_PLIES; ++k)
+                policy_off_out[g * (BK_MAX_PLIES + 1) + k] = int32_t(k <= plies ? off[g * (BK_HIST_CAP + 1) + k] : h[g].pol_count);
+        if ((policy_tile_out || policy_visits_out) && int64_t(h[g].pol_count) > int64_t(policy_cap))
+            return bk_fail(BK_ERR_CAPACITY, "bk_selfplay_results: policy_cap too small");
+        if (policy_tile_out && h[g].pol_count)
+            BK_CUDA(cudaMemcpyAsync(policy_tile_out + g * size_t(policy_cap), sp->d_pol_tile + g * size_t(sp->dcfg.policy_cap),
+                                    sizeof(uint16_t) * h[g].pol_count, cudaMemcpyDeviceToHost, sp->env->stream));
+        if (policy_visits_out && h[g].pol_count)
+            BK_CUDA(cudaMemcpyAsync(policy_visits_out + g * size_t(policy_cap), sp->d_pol_visits + g * size_t(sp->dcfg.policy_cap),
+                                    sizeof(uint32_t) * h[g].pol_count, cudaMemcpyDeviceToHost, sp->env->stream));
+    }
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    return BK_OK;
+}
+
+int bk_selfplay_last_root(bk_selfplay* sp, int32_t* counts_out, int16_t* tile_out, uint32_t* visits_out,
+                          float* value_sum_out, float* prior_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    const size_t n = size_t(sp->n);
+    int32_t* d_counts = sp->env->d_i32;
+    uint8_t* base = sp->d_stage;
+    uint32_t* d_vis = reinterpret_cast<uint32_t*>(base);
+    float* d_w = reinterpret_cast<float*>(base + n * 400 * 4);
+    float* d_p = reinterpret_cast<float*>(base + n * 400 * 8);
+    int16_t* d_tile = reinterpret_cast<int16_t*>(base + n * 400 * 12);
+    cudaStream_t st = sp->env->stream;
+    BK_LAUNCH(k_last_root, sp->n, 128, st, sp->dcfg, pools_of(sp), sp->n, d_counts, d_tile, d_vis, d_w, d_p);
+    BK_CUDA(cudaGetLastError());
+    if (counts_out) BK_CUDA(cudaMemcpyAsync(counts_out, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (tile_out) BK_CUDA(cudaMemcpyAsync(tile_out, d_tile, sizeof(int16_t) * 400 * n, cudaMemcpyDeviceToHost, st));
+    if (visits_out) BK_CUDA(cudaMemcpyAsync(visits_out, d_vis, sizeof(uint32_t) * 400 * n, cudaMemcpyDeviceToHost, st));
+    if (value_sum_out) BK_CUDA(cudaMemcpyAsync(value_sum_out, d_w, sizeof(float) * 400 * n, cudaMemcpyDeviceToHost, st));
+    if (prior_out) BK_CUDA(cudaMemcpyAsync(prior_out, d_p, sizeof(float) * 400 * n, cudaMemcpyDeviceToHost, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    return BK_OK;
+}
+
+int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    unsigned long long h[6];
+    BK_CUDA(cudaMemcpy(h, sp->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) out[i] = h[i];
+    return BK_OK;
+}
+
+int bk_selfplay_last_kernel_ms(bk_selfplay* sp, float* ms_out) {
+    if (!sp || !ms_out) return bk_fail(BK_ERR_INVALID_ARG, "null argument");
+    *ms_out = sp->last_ms;
+    return BK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// bk_mcts_kernels.cuh — warp-per-game MCTS self-play (self_play/src/simulation.rs:37-296,
+// self_play/src/node.rs:8-41) for sm_100a.
+//
+// Tree layout (per game, in HBM).  A reference `Node` is one CHILD ENTRY of its parent; entries of one
+// parent are contiguous and in ascending tile order (the canonical stand-in for HashMap iteration,
+// SURVEY.md Appendix D):
+//     N[cap] u32 visits | W[cap] f32 value_sum | P[cap] f32 prior | TN[cap] u32 = tile | node << 16
+// (struct of arrays: lane i of a select reads N[off+i], W[off+i], P[off+i] — three coalesced loads).
+// An entry that has been expanded points (node) into the node table, whose records are full game states
+// (BkState) plus the child block offset/count.  Keeping the state of every expanded node in HBM replaces
+// the reference's "clone the game and replay the path" (simulation.rs:196-203) by ONE Game::apply per
+// simulation — same states, same results, depth-times less rules work; 180 GB of HBM pays for it.
+//
+// Exactness (parity mode, the only mode here): one simulation in flight per game, simulations of a game
+// in order; f32 UCB arithmetic with explicit round-to-nearest ops in the reference's source order
+// (simulation.rs:88-98), the ln/sqrt factor from a host-built table indexed by parent visits, ties
+// resolved to the highest tile (`>=` over ascending order, simulation.rs:141).
+#pragma once
+#include "bk_env_kernels.cuh"
+
+#define BK_PATH_CAP 128
+#define BK_NODE_NONE 0xFFFFu
+
+#define BK_SP_ERR_ENTRY_CAP 1u
+#define BK_SP_ERR_PATH_CAP 2u
+#define BK_SP_ERR_NO_CHILD 4u   // select found no child with score >= 0 (reference would unwrap None)
+#define BK_SP_ERR_POLICY_CAP 8u
+#define BK_SP_ERR_APPLY 16u
+
+struct BkSearchCfg {
+    uint32_t sims, sample_moves;
+    float frac, alpha;
+    uint64_t seed;
+    uint32_t first_game_id;
+    uint32_t max_nodes, entry_cap, policy_cap;
+    const float* ucb_tab;    // [sims + 2]: (ln((N + c_base + 1)/c_base) + c_init) * sqrt(N), host libm
+    const float* prior_tab;  // [401]: stub prior for n children = e / (e + e + ... n times), f32 sequential
+    float stub_value;        // 0.25
+};
+
+struct BkTree {
+    uint32_t* N;
+    float* W;
+    float* P;
+    uint32_t* TN;
+    BkState* nodes;   // [max_nodes]; pad[0] = child offset, pad[1] = child count
+    double* scratch;  // [400]
+};
+
+// persisted per game between launches
+struct BkSearchHdr {
+    uint32_t n_nodes, n_entries, root_visits, sims_done;
+    uint32_t pend_kind, pend_depth, pend_parent, pend_tile;  // 0 none, 1 root, 2 leaf awaiting evaluator
+    uint32_t err, pol_count, plies_searched, pend_entry;
+    uint32_t path[BK_PATH_CAP];
+    uint8_t path_tp[BK_PATH_CAP];
+};
+
+struct BkSpCounters {  // lane-0 partial sums
+    uint32_t sims, applies, entries, nodes;
+};
+
+// per-warp shared scratch
+struct BkWarpSmem {
+    float e[400];
+    uint16_t tile[400];
+    uint32_t path[BK_PATH_CAP];
+    uint8_t path_tp[BK_PATH_CAP];
+};
+
+// f32 exp as the oracle defines it: exp in f64, rounded once to f32 (see oracle/mcts_oracle.hpp exp_f32)
+__device__ __forceinline__ float bk_exp_f32(float x) { return float(exp(double(x))); }
+
+__device__ __forceinline__ float bk_sel4f(int p, float a, float b, float c, float d) {
+    return p == 0 ? a : (p == 1 ? b : (p == 2 ? c : d));
+}
+
+// index of abs tile (r, c) inside the mover-frame policy vector (inverse of game.rs:77-89 rotation,
+// i.e. what simulation.rs:25-34 undoes `cur` times)
+__device__ __forceinline__ int bk_frame_index(int r, int c, int cur) {
+    if (cur == 0) return r * 20 + c;
+    if (cur == 1) return (19 - c) * 20 + r;
+    if (cur == 2) return (19 - r) * 20 + (19 - c);
+    return c * 20 + (19 - r);
+}
+
+// evaluate()'s expansion half (simulation.rs:66-81): children for the legal tiles of state L (with
+// policy > 0 when a policy is given), priors exp(p)/sum exp(p) summed sequentially in ascending order.
+// Writes state L to node slot `hdr.n_nodes` and returns that node id, or BK_NODE_NONE when the state
+// yields no child (the node then stays unexpanded, as in the reference) or a pool overflowed.
+__device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
+                                                   const BkRegs& L, const float* policy, int lane, BkWarpSmem& sm,
+                                                   BkSpCounters& ctr) {
+    const int cur = bk_cur(L);
+    // per-lane pass over this row's legal tiles
+    uint32_t m = L.legal;
+    int cnt = 0;
+    uint32_t keep = 0u;
+    if (policy) {
+        uint32_t mm = m;
+        while (mm) {
+            const int c = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            const float p = policy[bk_frame_index(lane, c, cur)];
+            if (p > 0.0f) { keep |= 1u << c; }
+        }
+        m = keep;
+    }
+    cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(BK_FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int n = __shfl_sync(BK_FULL, incl, 31);
+    int pos = incl - cnt;
+    {
+        uint32_t mm = m;
+        while (mm) {
+            const int c = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            sm.tile[pos] = uint16_t(lane * 20 + c);
+            if (policy) sm.e[pos] = bk_exp_f32(policy[bk_frame_index(lane, c, cur)]);
+            ++pos;
+        }
+    }
+    __syncwarp();
+    if (n == 0) return BK_NODE_NONE;
+    if (hd.n_entries + uint32_t(n) > cfg.entry_cap || hd.n_nodes >= cfg.max_nodes) {
+        hd.err |= BK_SP_ERR_ENTRY_CAP;
+        return BK_NODE_NONE;
+    }
+    float total = 0.0f;
+    if (policy) {
+        for (int i = 0; i < n; ++i) total = __fadd_rn(total, sm.e[i]);  // simulation.rs:74, ascending order
+    }
+    const uint32_t off = hd.n_entries;
+    const uint32_t id = hd.n_nodes;
+    for (int i = lane; i < n; i += 32) {
+        tr.N[off + i] = 0u;
+        tr.W[off + i] = 0.0f;
+        tr.P[off + i] = policy ? __fdiv_rn(sm.e[i], total) : cfg.prior_tab[n];
+        tr.TN[off + i] = uint32_t(sm.tile[i]) | (BK_NODE_NONE << 16);
+    }
+    BkState* ns = &tr.nodes[id];
+    bk_store(ns, lane, L);
+    if (lane == 0) { ns->pad[0] = off; ns->pad[1] = uint32_t(n); }
+    hd.n_entries += uint32_t(n);
+    hd.n_nodes += 1u;
+    if (lane == 0) { ctr.entries += uint32_t(n); ctr.nodes += 1u; }
+    __syncwarp();
+    return id;
+}
+
+// add_exploration_noise (simulation.rs:101-114) on the root's child block
+__device__ __forceinline__ void bk_tree_noise(const BkTree& tr, const BkSearchCfg& cfg, uint32_t game_id, uint32_t ply,
+                                              int lane) {
+    const uint32_t off = tr.nodes[0].pad[0];
+    const int n = int(tr.nodes[0].pad[1]);
+    if (n <= 1) return;
+    double mx = -1.0e300;
+    for (int i = lane; i < n; i += 32) {
+        const double lg = bk_log_gamma_draw(cfg.seed, game_id, ply, uint32_t(i), double(cfg.alpha));
+        tr.scratch[i] = lg;
+        mx = lg > mx ? lg : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double o = __shfl_xor_sync(BK_FULL, mx, d);
+        mx = o > mx ? o : mx;
+    }
+    for (int i = lane; i < n; i += 32) tr.scratch[i] = bk_det_exp(__dadd_rn(tr.scratch[i], -mx));
+    __syncwarp();
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, tr.scratch[i]);
+    const float keepf = __fsub_rn(1.0f, cfg.frac);
+    for (int i = lane; i < n; i += 32) {
+        const float noise = float(__ddiv_rn(tr.scratch[i], sum));
+        tr.P[off + i] = __fadd_rn(__fmul_rn(tr.P[off + i], keepf), __fmul_rn(noise, cfg.frac));
+    }
+    __syncwarp();
+}
+
+struct BkLeaf {
+    uint32_t parent;  // node whose child entry is the leaf
+    uint32_t entry;   // entry index of the leaf
+    int tile;
+    int depth;        // path length (>= 1)
+    bool ok;
+};
+
+// the selection loop of mcts() (simulation.rs:198-203) with select_child/ucb_score (:88-98,:135-147)
+__device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, int lane,
+                                                 BkWarpSmem& sm) {
+    BkLeaf lf;
+    lf.ok = true;
+    uint32_t node = 0u;
+    uint32_t Np = hd.root_visits;
+    int depth = 0;
+    for (;;) {
+        const BkState* ns = &tr.nodes[node];
+        const uint32_t off = ns->pad[0];
+        const int n = int(ns->pad[1]);
+        const float F = cfg.ucb_tab[Np];
+        float best = 0.0f;
+        int bi = -1;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t nc = tr.N[off + i];
+            const float w = tr.W[off + i];
+            const float pr = tr.P[off + i];
+            const float fn = float(nc);
+            const float q = nc ? __fdiv_rn(w, fn) : 0.0f;                       // node.rs:33-39
+            const float u = __fdiv_rn(F, __fadd_rn(1.0f, fn));                  // simulation.rs:92-94
+            const float sc = __fadd_rn(__fmul_rn(u, pr), q);                    // simulation.rs:95-97
+            if (sc >= best) { best = sc; bi = i; }                              // simulation.rs:141
+        }
+        const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
+        const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
+        if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
+        const uint32_t wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
+        const uint32_t e = off + wi;
+        const uint32_t tn = tr.TN[e];
+        if (depth >= BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; break; }
+        const uint32_t child = tn >> 16;
+        if (lane == 0) sm.path[depth] = e;
+        ++depth;
+        if (child == BK_NODE_NONE) {
+            lf.parent = node;
+            lf.entry = e;
+            lf.tile = int(tn & 0xFFFFu);
+            break;
+        }
+        if (lane == 0) sm.path_tp[depth - 1] = uint8_t(tr.nodes[child].meta & 3u);
+        Np = tr.N[e];
+        node = child;
+    }
+    lf.depth = depth;
+    __syncwarp();
+    return lf;
+}
+
+// backpropagate (simulation.rs:164-171): every entry on the path gets +1 visit and the value of the seat
+// to move AT that node (0 for a terminal / unexpanded leaf, node.rs:20)
+__device__ __forceinline__ void bk_tree_backup(const BkTree& tr, int depth, const float (&val)[4], int lane,
+                                               const BkWarpSmem& sm) {
+    for (int d = lane; d < depth; d += 32) {
+        const uint32_t e = sm.path[d];
+        const int tp = int(sm.path_tp[d]);
+        tr.N[e] += 1u;
+        tr.W[e] = __fadd_rn(tr.W[e], bk_sel4f(tp, val[0], val[1], val[2], val[3]));
+    }
+    __syncwarp();
+}
+
+// the tail of mcts() + select_action (simulation.rs:213-229, :118-130, :150-161): record the root's visit
+// distribution, then pick the tile to play.
+__device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
+                                                  uint32_t game_id, uint32_t ply, uint32_t* pol_off, uint16_t* pol_tile,
+                                                  uint32_t* pol_visits, int lane) {
+    const uint32_t off = tr.nodes[0].pad[0];
+    const int n = int(tr.nodes[0].pad[1]);
+    const uint32_t k = hd.plies_searched;
+    // policy record
+    if (hd.pol_count + uint32_t(n) > cfg.policy_cap || k >= BK_HIST_CAP) {
+        hd.err |= BK_SP_ERR_POLICY_CAP;
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            pol_tile[hd.pol_count + i] = uint16_t(tr.TN[off + i] & 0xFFFFu);
+            pol_visits[hd.pol_count + i] = tr.N[off + i];
+        }
+        if (lane == 0) { pol_off[k] = hd.pol_count; pol_off[k + 1] = hd.pol_count + uint32_t(n); }
+        hd.pol_count += uint32_t(n);
+    }
+    hd.plies_searched = k + 1u;
+    int pick = -1;
+    if (hd.plies_searched < cfg.sample_moves) {
+        uint32_t total = 0u;
+        for (int i = lane; i < n; i += 32) total += tr.N[off + i];
+        total = __reduce_add_sync(BK_FULL, total);
+        const float u = bk_action_uniform(cfg.seed, game_id, ply);
+        const float ft = float(total);
+        float sum = 0.0f;
+        for (int i = 0; i < n; ++i) {                                            // simulation.rs:123-128
+            sum = __fadd_rn(sum, __fdiv_rn(float(tr.N[off + i]), ft));
+            if (sum > u) { pick = i; break; }
+        }
+        if (pick < 0) pick = n - 1;                                              // simulation.rs:129
+    } else {
+        uint32_t bestv = 0u;
+        int bi = -1;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t v = tr.N[off + i];
+            if (v >= bestv) { bestv = v; bi = i; }                               // max_by keeps the last maximum
+        }
+        const uint32_t key = bi >= 0 ? bestv + 1u : 0u;
+        const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
+        pick = int(__reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u)) - 1;
+    }
+    return int(tr.TN[off + uint32_t(pick)] & 0xFFFFu);
+}
+
+// One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
+// evaluate (terminal payoff, or stub value + expansion), back up.
+__device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, int lane,
+                                            const BkTabs& tabs, BkWarpSmem& sm, BkCounters& gctr, BkSpCounters& ctr) {
+    hd.root_visits += 1u;                                                        // simulation.rs:194
+    const BkLeaf lf = bk_tree_select(tr, hd, cfg, lane, sm);
+    if (!lf.ok) return;
+    BkRegs L;
+    bk_load(&tr.nodes[lf.parent], lane, L);
+    if (!bk_apply(L, lf.tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; return; }
+    if (lane == 0) ctr.applies += 1u;
+    float val[4];
+    int tp = 0;
+    if (bk_terminal(L)) {
+        bk_payoff(L, val);                                                       // simulation.rs:45-47
+    } else {
+        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, nullptr, lane, sm, ctr);
+        if (id != BK_NODE_NONE && lane == 0) tr.TN[lf.entry] = uint32_t(lf.tile) | (id << 16);
+        tp = bk_cur(L);                                                          // simulation.rs:78
+        val[0] = val[1] = val[2] = val[3] = cfg.stub_value;
+    }
+    if (lane == 0) sm.path_tp[lf.depth - 1] = uint8_t(tp);
+    __syncwarp();
+    bk_tree_backup(tr, lf.depth, val, lane, sm);
+    hd.sims_done += 1u;
+    if (lane == 0) ctr.sims += 1u;
+}
+
+// training_game() (simulation.rs:267-296) with the stub evaluator, up to max_plies plies, on one warp.
+__device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState* __restrict__ states,
+                                                 uint16_t* __restrict__ hist, const BkTree& tr, BkSearchHdr* hdr_g,
+                                                 uint32_t* pol_off, uint16_t* pol_tile, uint32_t* pol_visits,
+                                                 int max_plies, unsigned long long* counters, int g, int lane,
+                                                 const BkTabs& tabs, BkWarpSmem& sm) {
+    BkRegs G;
+    bk_load(&states[g], lane, G);
+    BkSearchHdr hd;
+    hd.err = hdr_g->err;
+    hd.pol_count = hdr_g->pol_count;
+    hd.plies_searched = hdr_g->plies_searched;
+    BkCounters gctr = {0u, 0u};
+    BkSpCounters ctr = {0u, 0u, 0u, 0u};
+    const uint32_t game_id = cfg.first_game_id + uint32_t(g);
+    int plies = 0;
+    while (!bk_terminal(G) && (max_plies < 0 || plies < max_plies) && hd.err == 0u) {
+        hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
+        bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr);                        // evaluate(root), :184
+        bk_tree_noise(tr, cfg, game_id, G.ply, lane);                                  // :190
+        for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, lane, tabs, sm, gctr, ctr);
+        if (hd.err) break;
+        const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
+        const int p = bk_cur(G);
+        const uint32_t ply = G.ply;
+        if (!bk_apply(G, action, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }   // :288
+        if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
+        ++plies;
+    }
+    bk_store(&states[g], lane, G);
+    if (lane == 0) {
+        hdr_g->err = hd.err;
+        hdr_g->pol_count = hd.pol_count;
+        hdr_g->plies_searched = hd.plies_searched;
+        hdr_g->n_nodes = hd.n_nodes;
+        hdr_g->n_entries = hd.n_entries;
+        hdr_g->root_visits = hd.root_visits;
+        hdr_g->sims_done = hd.sims_done;
+        hdr_g->pend_kind = 0u;
+    }
+    const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
+    if (lane == 0 && counters) {
+        atomicAdd(&counters[0], (unsigned long long)ctr.sims);
+        atomicAdd(&counters[1], (unsigned long long)ctr.applies + (unsigned long long)plies);
+        atomicAdd(&counters[2], (unsigned long long)gctr.movegens);
+        atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
+        atomicAdd(&counters[4], (unsigned long long)ctr.entries);
+        atomicAdd(&counters[5], (unsigned long long)ctr.nodes);
+    }
+}

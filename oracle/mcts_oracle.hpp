@@ -62,6 +62,12 @@ inline void stub_evaluator(int, const Planes& planes, std::vector<float>& policy
     value.assign(4, 0.25f);
 }
 
+// f32 exp.  The reference calls f32::exp (simulation.rs:71), i.e. the platform libm's expf, whose last
+// bit is not specified (glibc documents 0.502 ULP).  Canonical form used by oracle AND kernels: exp in
+// f64, rounded once to f32 — correctly rounded except for ~2^-29 double-rounding cases, and the same on
+// a CPU and a GPU for the arguments that occur.
+inline float exp_f32(float x) { return float(std::exp(double(x))); }
+
 // simulation.rs:25-34
 inline std::vector<float> rotate_policy(const std::vector<float>& state) {
     std::vector<float> rotated(400, 0.0f);
@@ -85,7 +91,7 @@ inline std::vector<float> evaluate(Node& node, const Game& game, const Evaluator
     }
     std::vector<std::pair<size_t, float>> exp_policy;
     for (size_t tile : game.get_legal_tiles())
-        if (policy[tile] > 0.0f) exp_policy.emplace_back(tile, std::exp(policy[tile]));
+        if (policy[tile] > 0.0f) exp_policy.emplace_back(tile, exp_f32(policy[tile]));
     float total = 0.0f;
     for (const auto& tp : exp_policy) total += tp.second;
     node.to_play = cur;

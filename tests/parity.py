@@ -193,3 +193,46 @@ def check_piece_to_finish(lib, orc, seed=0, n_steps=60):
         st = batch.apply([lt[0]], [21], strict=False)
         assert st[0] == -3 and batch.digest()[0] == before
     batch.close()
+
+
+def check_selfplay_stub(lib, orc, n_games, cfg_kwargs, first_game_id=0, max_plies=-1, n_check=None):
+    """training_game() with the fixed-prior stub: per-ply root visit vectors, action trace, priors and
+    value sums of the last root — all bit-exact against the oracle (visit counts exact; Q = W/N follows)."""
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(**cfg_kwargs)
+    ocfg = orc.make_config(cfg.sims_per_move, cfg.sample_moves, float(cfg.c_base), float(cfg.c_init),
+                           float(cfg.dirichlet_alpha), float(cfg.exploration_fraction), cfg.seed)
+    sp = SelfPlay(n_games, cfg, first_game_id=first_game_id, lib=lib)
+    sp.run_stub(max_plies)
+    recs = sp.policy_records()
+    hist = sp.env.history()
+    roots = sp.last_root()
+    pay = sp.env.payoff()
+    term = sp.env.is_terminal()
+    ctr = sp.counters()
+    idx = range(n_games) if n_check is None else np.linspace(0, n_games - 1, n_check).astype(int)
+    for g in idx:
+        ref = orc.selfplay_game(ocfg, first_game_id + int(g), max_plies=max_plies)
+        assert ref["n_plies"] == len(recs[g]), (g, ref["n_plies"], len(recs[g]))
+        assert [t for _, t in hist[g]] == ref["tiles"].tolist(), f"action trace differs, game {g}"
+        assert [p for p, _ in hist[g]] == ref["players"].tolist()
+        for k in range(ref["n_plies"]):
+            tiles, visits = recs[g][k]
+            assert np.array_equal(tiles, ref["roots"][k]["tile"]), f"root children differ, game {g} ply {k}"
+            assert np.array_equal(visits, ref["roots"][k]["visits"]), f"visit counts differ, game {g} ply {k}"
+            assert int(visits.sum()) == cfg.sims_per_move
+        last = ref["roots"][-1]
+        assert np.array_equal(roots[g]["tile"], last["tile"])
+        assert np.array_equal(roots[g]["visits"], last["visits"])
+        assert np.array_equal(roots[g]["prior"], last["prior"]), f"priors (Dirichlet noise) differ, game {g}"
+        # Q within 1e-5 relative (north star); in fact the f32 value sums are identical
+        q_dev = roots[g]["value_sum"] / np.maximum(roots[g]["visits"], 1)
+        q_ref = last["value_sum"] / np.maximum(last["visits"], 1)
+        assert np.allclose(q_dev, q_ref, rtol=1e-5, atol=0)
+        assert np.array_equal(roots[g]["value_sum"], last["value_sum"])
+        if max_plies < 0:
+            assert term[g] and pay[g].tolist() == ref["payoff"].tolist()
+    total_plies = sum(len(r) for r in recs)
+    assert ctr["sims"] == total_plies * cfg.sims_per_move
+    sp.close()
+    return {"plies": total_plies, "counters": ctr}

@@ -1,0 +1,68 @@
+"""MCTS parity tests proper: the sm_100a build through the C ABI against the CPU oracle.
+North star: visit counts exact under fixed priors and seeded noise, Q within 1e-5 relative."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+CONFIG3 = dict(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+               exploration_fraction=0.25, seed=20261018)
+
+
+def test_gpu_selfplay_full_games_64_sims(cuda_lib, orc):
+    """Whole games to the end (every ply's root visit vector + action trace + payoff)."""
+    r = parity.check_selfplay_stub(cuda_lib, orc, 6, dict(CONFIG3, sims_per_move=64, seed=11), first_game_id=100)
+    assert r["plies"] > 6 * 230
+
+
+def test_gpu_selfplay_config3_prefix(cuda_lib, orc):
+    """BASELINE.json config 3 parameters (800 sims, alpha 0.03, frac 0.25), first plies of a few games."""
+    parity.check_selfplay_stub(cuda_lib, orc, 64, CONFIG3, first_game_id=0, max_plies=5, n_check=4)
+
+
+def test_gpu_selfplay_shipped_config(cuda_lib, orc):
+    """model/training.py:267-272: 50 sims, alpha 0.3, sample_moves 30."""
+    parity.check_selfplay_stub(cuda_lib, orc, 4, dict(sims_per_move=50, sample_moves=30, c_base=19652, c_init=1.25,
+                                                     dirichlet_alpha=0.3, exploration_fraction=0.25, seed=5))
+
+
+def test_gpu_selfplay_resume_equals_one_run(cuda_lib, orc):
+    """max_plies prefixes compose: 3 + 4 plies == 7 plies."""
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(**dict(CONFIG3, sims_per_move=100))
+    a = SelfPlay(16, cfg, lib=cuda_lib)
+    a.run_stub(3)
+    a.run_stub(4)
+    b = SelfPlay(16, cfg, lib=cuda_lib)
+    b.run_stub(7)
+    assert a.env.history() == b.env.history()
+    ra, rb = a.policy_records(), b.policy_records()
+    for g in range(16):
+        assert len(ra[g]) == len(rb[g]) == 7
+        for (t1, v1), (t2, v2) in zip(ra[g], rb[g]):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+
+
+def test_gpu_selfplay_1024_games_invariants(cuda_lib, orc):
+    """Config 3 at full width (1024 games, 800 sims) for two plies: tree invariants for every game and
+    sharding invariance (a 256-game shard at id 512 equals that slice of the full batch)."""
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(**CONFIG3)
+    sp = SelfPlay(1024, cfg, lib=cuda_lib)
+    sp.run_stub(2)
+    recs = sp.policy_records()
+    for g in range(1024):
+        assert len(recs[g]) == 2
+        for tiles, visits in recs[g]:
+            assert int(visits.sum()) == 800 and np.all(np.diff(tiles) > 0)
+    c = sp.counters()
+    assert c["sims"] == 1024 * 2 * 800 and c["nodes"] <= c["sims"] + 2 * 1024
+    shard = SelfPlay(256, cfg, first_game_id=512, lib=cuda_lib)
+    shard.run_stub(2)
+    rs = shard.policy_records()
+    for g in range(256):
+        for (t1, v1), (t2, v2) in zip(rs[g], recs[512 + g]):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    assert shard.env.history() == sp.env.history()[512:768]
