@@ -121,6 +121,43 @@ def cpu_baseline(target_seconds: float = 12.0) -> dict:
                       f"{res['steps']} moves in {res['seconds']:.2f} s"}
 
 
+MCTS_GAMES = 1024
+MCTS_CFG = dict(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                exploration_fraction=0.25, seed=SEED)
+
+
+def mcts_measure(local_rank: int, rank: int, plies: int):
+    """Secondary metric (BASELINE.json configs[2]): 1024 games/GPU, 800 sims/move, fixed uniform priors,
+    Dirichlet alpha 0.03 / frac 0.25, the whole self-play loop on the device.  plies < 0: complete games."""
+    from blokus_self_play import SelfPlay, Config
+    sp = SelfPlay(MCTS_GAMES, Config(**MCTS_CFG), first_game_id=rank * MCTS_GAMES, device=local_rank)
+    sp.run_stub(2)                      # warm-up (2 plies), then start over
+    sp.reset()
+    c0 = sp.counters()
+    ms = sp.run_stub(plies)
+    c1 = sp.counters()
+    out = {k: c1[k] - c0[k] for k in c1}
+    out["kernel_ms"] = ms
+    out["plies"] = int(sum(len(h) for h in sp.env.history()))
+    out["finished_games"] = int(sp.env.is_terminal().sum())
+    sp.close()
+    return out
+
+
+def mcts_cpu_baseline(target_seconds: float = 10.0) -> dict:
+    from oracle import oracle as orc
+    thr = host_threads()
+    cfg = orc.make_config(**{**MCTS_CFG, "c_base": 19652.0})
+    plies = 2
+    r = orc.selfplay_batch(cfg, 0, thr, n_threads=thr, max_plies=plies)
+    rate = r["sims"] / max(r["seconds"], 1e-9)
+    plies = int(max(2, min(24, target_seconds * rate / (800.0 * thr))))
+    r = orc.selfplay_batch(cfg, 0, thr, n_threads=thr, max_plies=plies)
+    return {"value": r["sims"] / r["seconds"], "unit": "sims/s", "cores": thr, "kind": "port",
+            "sample": f"first {plies} plies of {thr} config-3 games (800 sims/move, stub evaluator) by the C++ restatement "
+                      f"of self_play/src/simulation.rs, one game per thread; {r['sims']} sims in {r['seconds']:.2f} s"}
+
+
 def run_reference(args) -> int:
     """--impl reference: the reference's CPU algorithm (oracle port; no Rust toolchain here) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +201,7 @@ def main() -> int:
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (default: configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true", help="skip the secondary MCTS sims/s measurement")
+    ap.add_argument("--mcts-plies", type=int, default=-1, help="plies per game in the MCTS measurement (<0: whole games)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -256,14 +294,26 @@ def main() -> int:
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # ---- secondary metric: MCTS sims/s (configs[2]) -------------------------------------------------
+    mcts = None
+    if not args.no_mcts:
+        batch.close()
+        del flush
+        torch.cuda.empty_cache()
+        barrier()
+        mcts = mcts_measure(local_rank, rank, args.mcts_plies)
+        barrier()
+
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
-    stats = torch.tensor([region_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
-    work = torch.tensor([moves, e2e_moves, lane_ops, movegens], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([region_ms, e2e_s, kernel_ms, mcts["kernel_ms"] if mcts else 0.0], dtype=torch.float64, device="cuda")
+    work = torch.tensor([moves, e2e_moves, lane_ops, movegens, mcts["sims"] if mcts else 0,
+                         mcts["plies"] if mcts else 0, mcts["finished_games"] if mcts else 0,
+                         mcts["lane_ops"] if mcts else 0, mcts["entries"] if mcts else 0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    region_ms, e2e_s, kernel_ms = stats.tolist()
-    moves, e2e_moves, lane_ops, movegens = work.tolist()
+    region_ms, e2e_s, kernel_ms, mcts_ms = stats.tolist()
+    moves, e2e_moves, lane_ops, movegens, mcts_sims, mcts_plies, mcts_done, mcts_lane_ops, mcts_entries = work.tolist()
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -307,8 +357,26 @@ def main() -> int:
             "clocks": clocks,
             "extra": {"movegens_per_move": movegens / max(moves, 1), "kernel_only_moves_per_s": moves / (kernel_ms * 1e-3)},
         }
+        if mcts:
+            line["gpu_launches"] += 1
+            line["extra"]["mcts"] = {
+                "metric": "mcts_sims_per_sec_fixed_priors", "value": mcts_sims / (mcts_ms * 1e-3), "unit": "sims/s",
+                "config": "configs[2]: 1024 games per GPU, 800 sims/move, fixed uniform priors (stub evaluator), Dirichlet "
+                          "alpha 0.03 frac 0.25, sample_moves 30; " + ("complete games" if args.mcts_plies < 0 else f"first {args.mcts_plies} plies"),
+                "sims": mcts_sims, "plies_searched": mcts_plies, "finished_games": mcts_done, "kernel_ms": mcts_ms,
+                "kernel": "k_selfplay_stub (one launch: every ply's root expansion, noise, 800 sims, action, apply)",
+                # ~1.6 KB algorithmic HBM bytes per simulation
+                "roofline": {"bound": "hbm", "achieved": 1600.0 * mcts_sims / world / (mcts_ms * 1e-3) / 1e9,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": 1600.0 * mcts_sims / world / (mcts_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None},
+                "int_roofline": {"achieved": mcts_lane_ops / world / (mcts_ms * 1e-3), "peak": int_peak, "unit": "lane-ops/s",
+                                 "frac": mcts_lane_ops / world / (mcts_ms * 1e-3) / int_peak},
+                "child_entries_created": mcts_entries,
+            }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if mcts:
+                line["extra"]["mcts"]["cpu_baseline"] = mcts_cpu_baseline()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(device_ids=[local_rank])

@@ -91,6 +91,7 @@ _SIGNATURES = {
     "bk_env_playout_counters": (C.c_int, [_P, _P]),
     "bk_selfplay_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(BkConfig), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "bk_selfplay_destroy": (None, [_P]),
+    "bk_selfplay_reset": (C.c_int, [_P, C.c_uint32]),
     "bk_selfplay_run_stub": (C.c_int, [_P, C.c_int]),
     "bk_selfplay_begin_ply": (C.c_int, [_P]),
     "bk_selfplay_leaf_planes": (C.c_int, [_P, _P, _P]),

@@ -62,6 +62,11 @@ class SelfPlay:
         except Exception:
             pass
 
+    def reset(self, first_game_id: Optional[int] = None) -> None:
+        if first_game_id is not None:
+            self.first_game_id = first_game_id
+        self.lib.check(self.lib.bk_selfplay_reset(self._h, self.first_game_id))
+
     def run_stub(self, max_plies: int = -1) -> float:
         """training_game() with the fixed-prior stub evaluator, on the device; returns kernel ms."""
         self.lib.check(self.lib.bk_selfplay_run_stub(self._h, max_plies))
@@ -83,7 +88,7 @@ class SelfPlay:
         return {"sims": int(c[0]), "applies": int(c[1]), "movegens": int(c[2]), "lane_ops": int(c[3]),
                 "entries": int(c[4]), "nodes": int(c[5])}
 
-    def policy_records(self, policy_cap: int = 16384):
+    def policy_records(self, policy_cap: int = 32768):
         """Per game, per searched ply: (tiles int16[k], visits uint32[k]) of the root's children."""
         plies = np.zeros(self.n, dtype=np.int32)
         off = np.zeros((self.n, _lib.MAX_PLIES + 1), dtype=np.int32)

@@ -141,7 +141,7 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     d.first_game_id = first_game_id;
     d.max_nodes = cfg->sims_per_move + 2u;
     d.entry_cap = max_children_per_game ? max_children_per_game : (cfg->sims_per_move + 2u) * 128u;
-    d.policy_cap = 16384u;
+    d.policy_cap = 32768u;
     d.stub_value = 0.25f;
     const size_t ne = size_t(n_games) * d.entry_cap;
     BK_CUDA(cudaMalloc(&sp->d_N, sizeof(uint32_t) * ne));
@@ -194,6 +194,18 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     if (sp->ev1) cudaEventDestroy(sp->ev1);
     bk_env_destroy(sp->env);
     delete sp;
+}
+
+int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    rc = bk_env_reset(sp->env);
+    if (rc) return rc;
+    sp->first_id = first_game_id;
+    sp->dcfg.first_game_id = first_game_id;
+    BK_CUDA(cudaMemset(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(sp->n)));
+    BK_CUDA(cudaMemset(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(sp->n)));
+    return BK_OK;
 }
 
 int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {

@@ -177,6 +177,8 @@ typedef struct bk_config {
 int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t first_game_id,
                        uint32_t max_children_per_game, bk_selfplay** out);
 void bk_selfplay_destroy(bk_selfplay* sp);
+/* Start every client over from Game::reset() with new global ids first_game_id.. (pools are reused). */
+int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id);
 /* training_game() with the fixed-prior stub evaluator (policy 1.0 on legal tiles, value 0.25 per
  * seat; BASELINE.json config 3) for up to max_plies more plies per game (< 0: to the end), fully on
  * the device: per ply mcts() = root evaluate, Dirichlet noise, sims_per_move x (select, apply,

@@ -1,0 +1,20 @@
+"""Small fixed workloads for `ncu --set full` captures (one GPU, a handful of launches)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "blokus-engine_b200"))
+from blokus_self_play import GameBatch, SelfPlay, Config
+
+what = sys.argv[1] if len(sys.argv) > 1 else "playout"
+if what == "playout":
+    b = GameBatch(4096)
+    for k in range(4):
+        b.reset()
+        r = b.playout(seed=k)
+    print("playout", r["total_steps"], r["kernel_ms"])
+else:
+    cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                 exploration_fraction=0.25, seed=1)
+    sp = SelfPlay(1024, cfg, max_children_per_game=16384)
+    for k in range(3):
+        ms = sp.run_stub(2)
+    print("mcts", sp.counters(), ms)
