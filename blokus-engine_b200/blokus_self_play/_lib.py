@@ -97,6 +97,7 @@ _SIGNATURES = {
     "bk_selfplay_leaf_planes": (C.c_int, [_P, _P, _P]),
     "bk_selfplay_expand_backup": (C.c_int, [_P, _P, _P, _P]),
     "bk_selfplay_end_ply": (C.c_int, [_P]),
+    "bk_selfplay_set_stream": (C.c_int, [_P, _P]),
     "bk_selfplay_live_games": (C.c_int, [_P, _P]),
     "bk_selfplay_env": (_P, [_P]),
     "bk_selfplay_results": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),

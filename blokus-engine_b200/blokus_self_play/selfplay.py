@@ -72,6 +72,63 @@ class SelfPlay:
         self.lib.check(self.lib.bk_selfplay_run_stub(self._h, max_plies))
         return self.last_kernel_ms()
 
+    # ---- external evaluator (simulation.rs:50-57 replaced by one device batch per round) ---------------
+    def set_stream(self, cuda_stream: int) -> None:
+        self.lib.check(self.lib.bk_selfplay_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def begin_ply(self) -> None:
+        self.lib.check(self.lib.bk_selfplay_begin_ply(self._h))
+
+    def leaf_planes(self, dev_planes_ptr: int, want_count: bool = True) -> int:
+        cnt = C.c_int32(0)
+        self.lib.check(self.lib.bk_selfplay_leaf_planes(self._h, C.c_void_p(dev_planes_ptr), C.byref(cnt) if want_count else None))
+        return cnt.value
+
+    def expand_backup(self, dev_policy_ptr: int, dev_value_ptr: int, want_count: bool = True) -> int:
+        cnt = C.c_int32(0)
+        self.lib.check(self.lib.bk_selfplay_expand_backup(self._h, C.c_void_p(dev_policy_ptr), C.c_void_p(dev_value_ptr),
+                                                          C.byref(cnt) if want_count else None))
+        return cnt.value
+
+    def end_ply(self) -> None:
+        self.lib.check(self.lib.bk_selfplay_end_ply(self._h))
+
+    def run_evaluator(self, evaluator: Callable, max_plies: int = -1, xp: str = "torch") -> dict:
+        """training_game() for every client with a caller-supplied evaluator.
+
+        evaluator(planes[n,5,20,20] float32) -> (policy[n,400] float32 in the mover's frame, value[n,4] float32
+        in relative-seat order), exactly the contract of the reference's inference server
+        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch.
+        xp="torch": CUDA tensors on this handle's device; xp="numpy": host arrays, valid only with the tests'
+        CPU-emulator build of the library (where "device" memory is host memory)."""
+        n = self.n
+        if xp == "torch":
+            import torch
+            dev = torch.device("cuda", self.env.device)
+            planes = torch.zeros((n, 5, 20, 20), dtype=torch.float32, device=dev)
+            self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            ptr = lambda t: t.data_ptr()
+            prep = lambda t: t.to(dtype=torch.float32).contiguous()
+        else:
+            planes = np.zeros((n, 5, 20, 20), dtype=np.float32)
+            ptr = lambda a: a.ctypes.data
+            prep = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        rounds = 0
+        plies = 0
+        while (max_plies < 0 or plies < max_plies) and self.live_games() > 0:
+            self.begin_ply()
+            pending = self.leaf_planes(ptr(planes))
+            while pending > 0:
+                policy, value = evaluator(planes)
+                policy, value = prep(policy), prep(value)
+                pending = self.expand_backup(ptr(policy), ptr(value))
+                rounds += 1
+                if pending > 0:
+                    self.leaf_planes(ptr(planes), want_count=False)
+            self.end_ply()
+            plies += 1
+        return {"plies": plies, "rounds": rounds}
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0)
         self.lib.check(self.lib.bk_selfplay_last_kernel_ms(self._h, C.byref(ms)))
@@ -144,5 +201,37 @@ def play_training_games(ids: Sequence[int], config, device: int = 0, lib: Option
     try:
         sp.run_stub(-1)
         return sp.game_data()
+    finally:
+        sp.close()
+
+
+def host_evaluator(fn: Callable):
+    """Adapt fn(planes: np.ndarray[n,5,20,20]) -> (policy np[n,400], value np[n,4]) to CUDA tensors."""
+    def wrapped(planes):
+        import torch
+        pol, val = fn(planes.detach().cpu().numpy())
+        return (torch.from_numpy(np.ascontiguousarray(pol, dtype=np.float32)).to(planes.device),
+                torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(planes.device))
+    return wrapped
+
+
+def play_training_game(id: int, config, inference_queue, pipe, device: int = 0, lib: Optional[Lib] = None):
+    """Drop-in for the reference's `play_training_game(id, config, inference_queue, pipe)`
+    (self_play/src/lib.rs:9-32): one game, every leaf sent to the Python inference server with the
+    reference's own protocol — `inference_queue.put((id, planes))` with planes as nested bool lists
+    [5][20][20] and `pipe.recv()` -> (policy[400], value[4]) (simulation.rs:50-57).  Returns
+    (history, policies, values).  This keeps `model/training.py` running unmodified; the batched
+    `SelfPlay.run_evaluator` is the fast path."""
+    sp = SelfPlay(1, config, first_game_id=int(id), device=device, lib=lib)
+
+    def ev(planes_np):
+        inference_queue.put((id, planes_np[0].astype(bool).tolist()))
+        policy, value = pipe.recv()
+        return np.asarray(policy, dtype=np.float32)[None, :], np.asarray(value, dtype=np.float32)[None, :]
+
+    try:
+        emulated = "emu" in sp.lib.path
+        sp.run_evaluator(ev if emulated else host_evaluator(ev), -1, xp="numpy" if emulated else "torch")
+        return sp.game_data()[0]
     finally:
         sp.close()

@@ -65,6 +65,62 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
                      counters, g, lane, tabs, wsm);
 }
 
+__global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl, const BkState* states, int n) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    kb_sp_begin(states, bk_tree_of(pl, cfg, g), &pl.hdr[g], g, lane);
+}
+
+// planes of every game's pending position, float32 [n][5][20][20]; counts pending games
+__global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, float* __restrict__ out, int32_t* __restrict__ pending) {
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const BkSearchHdr* h = &pl.hdr[g];
+    const bool pend = h->pend_kind == BK_PEND_ROOT || h->pend_kind == BK_PEND_LEAF;
+    float* o = out + size_t(g) * 2000;
+    if (pend) {
+        kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[h->n_nodes], o, threadIdx.x, blockDim.x);
+        if (threadIdx.x == 0) atomicAdd(pending, 1);
+    } else {
+        for (int e = threadIdx.x; e < 2000; e += blockDim.x) o[e] = 0.0f;
+    }
+}
+
+__global__ void k_sp_count(BkPools pl, int n, int32_t* __restrict__ counts) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const uint32_t k = pl.hdr[g].pend_kind;
+    if (k == BK_PEND_ROOT || k == BK_PEND_LEAF) atomicAdd(&counts[0], 1);
+    if (k == BK_PEND_DONE) atomicAdd(&counts[1], 1);
+}
+
+__global__ void __launch_bounds__(32)
+k_sp_step(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* value, unsigned long long* counters) {
+    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ BkWarpSmem wsm;
+    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    kb_sp_step(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], policy, value, counters, g, lane, tabs, wsm);
+}
+
+__global__ void __launch_bounds__(32)
+k_sp_end(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, unsigned long long* counters) {
+    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ BkWarpSmem wsm;
+    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    kb_sp_end(cfg, states, hist, bk_tree_of(pl, cfg, g), &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+              pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, counters, g, lane, tabs,
+              wsm);
+}
+
 // gather the root's child block (tile, visits, value_sum, prior) of every game: out[g][400] x 4 arrays
 __global__ void k_last_root(BkSearchCfg cfg, BkPools pl, int n, int32_t* counts, int16_t* tile, uint32_t* visits,
                             float* wsum, float* prior) {
@@ -222,11 +278,84 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     return sp_check_errors(sp);
 }
 
-#define BK_NOT_YET(name) return bk_fail(BK_ERR_STATE, name ": not implemented yet")
-int bk_selfplay_begin_ply(bk_selfplay*) { BK_NOT_YET("bk_selfplay_begin_ply"); }
-int bk_selfplay_leaf_planes(bk_selfplay*, float*, int32_t*) { BK_NOT_YET("bk_selfplay_leaf_planes"); }
-int bk_selfplay_expand_backup(bk_selfplay*, const float*, const float*, int32_t*) { BK_NOT_YET("bk_selfplay_expand_backup"); }
-int bk_selfplay_end_ply(bk_selfplay*) { BK_NOT_YET("bk_selfplay_end_ply"); }
+static int sp_counts(bk_selfplay* sp, int32_t* pending, int32_t* done) {
+    int32_t* d = sp->env->d_i32;
+    cudaStream_t st = sp->env->stream;
+    BK_CUDA(cudaMemsetAsync(d, 0, sizeof(int32_t) * 2, st));
+    BK_LAUNCH(k_sp_count, (sp->n + 127) / 128, 128, st, pools_of(sp), sp->n, d);
+    BK_CUDA(cudaGetLastError());
+    int32_t h[2];
+    BK_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    if (pending) *pending = h[0];
+    if (done) *done = h[1];
+    return BK_OK;
+}
+
+int bk_selfplay_begin_ply(bk_selfplay* sp) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    BK_LAUNCH(k_sp_begin, (sp->n + 3) / 4, 128, sp->env->stream, sp->dcfg, pools_of(sp), sp->env->d_states, sp->n);
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!dev_planes) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_leaf_planes: dev_planes is null");
+    cudaStream_t st = sp->env->stream;
+    int32_t* d_cnt = sp->env->d_i32 + 2;
+    BK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t), st));
+    BK_LAUNCH(k_sp_planes, sp->n, 256, st, sp->dcfg, pools_of(sp), sp->n, dev_planes, d_cnt);
+    BK_CUDA(cudaGetLastError());
+    if (pending_out) {
+        BK_CUDA(cudaMemcpyAsync(pending_out, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BK_CUDA(cudaStreamSynchronize(st));
+    }
+    return BK_OK;
+}
+
+int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* pending_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!dev_policy || !dev_value) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_expand_backup: null evaluator output");
+    cudaStream_t st = sp->env->stream;
+    BK_CUDA(cudaEventRecord(sp->ev0, st));
+    BK_LAUNCH(k_sp_step, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, dev_policy, dev_value, sp->d_counters);
+    BK_CUDA(cudaEventRecord(sp->ev1, st));
+    BK_CUDA(cudaGetLastError());
+    if (pending_out) {
+        rc = sp_counts(sp, pending_out, nullptr);
+        if (rc) return rc;
+        BK_CUDA(cudaEventElapsedTime(&sp->last_ms, sp->ev0, sp->ev1));
+    }
+    return BK_OK;
+}
+
+int bk_selfplay_end_ply(bk_selfplay* sp) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    int32_t pending = 0;
+    rc = sp_counts(sp, &pending, nullptr);
+    if (rc) return rc;
+    if (pending) return bk_fail(BK_ERR_STATE, "bk_selfplay_end_ply: some games still wait for the evaluator");
+    BK_LAUNCH(k_sp_end, sp->n, 32, sp->env->stream, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+              sp->d_counters);
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    return sp_check_errors(sp);
+}
+
+int bk_selfplay_set_stream(bk_selfplay* sp, void* cuda_stream) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    if (sp->env->stream && !sp->env->borrowed) cudaStreamDestroy(sp->env->stream);
+    sp->env->stream = static_cast<cudaStream_t>(cuda_stream);
+    sp->env->borrowed = true;
+    return BK_OK;
+}
 
 int bk_selfplay_live_games(bk_selfplay* sp, int32_t* out) {
     int rc = sp_use(sp);

@@ -378,3 +378,145 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         atomicAdd(&counters[5], (unsigned long long)ctr.nodes);
     }
 }
+
+// ---- external-evaluator protocol (one leaf per live game per round) ---------------------------------------
+// pend_kind values
+#define BK_PEND_NONE 0u   // no ply in progress (or the game is over)
+#define BK_PEND_ROOT 1u   // root position waiting for the evaluator          (simulation.rs:183-189)
+#define BK_PEND_LEAF 2u   // a leaf position waiting for the evaluator         (simulation.rs:206)
+#define BK_PEND_DONE 3u   // all simulations of this ply are done; waiting for bk_selfplay_end_ply
+
+__device__ __forceinline__ void bk_hdr_load(const BkSearchHdr* h, BkSearchHdr& hd, int lane, BkWarpSmem& sm) {
+    hd.n_nodes = h->n_nodes; hd.n_entries = h->n_entries; hd.root_visits = h->root_visits; hd.sims_done = h->sims_done;
+    hd.pend_kind = h->pend_kind; hd.pend_depth = h->pend_depth; hd.pend_parent = h->pend_parent; hd.pend_tile = h->pend_tile;
+    hd.err = h->err; hd.pol_count = h->pol_count; hd.plies_searched = h->plies_searched; hd.pend_entry = h->pend_entry;
+    for (int d = lane; d < int(hd.pend_depth) && d < BK_PATH_CAP; d += 32) { sm.path[d] = h->path[d]; sm.path_tp[d] = h->path_tp[d]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void bk_hdr_store(BkSearchHdr* h, const BkSearchHdr& hd, int lane, const BkWarpSmem& sm) {
+    __syncwarp();
+    for (int d = lane; d < int(hd.pend_depth) && d < BK_PATH_CAP; d += 32) { h->path[d] = sm.path[d]; h->path_tp[d] = sm.path_tp[d]; }
+    if (lane == 0) {
+        h->n_nodes = hd.n_nodes; h->n_entries = hd.n_entries; h->root_visits = hd.root_visits; h->sims_done = hd.sims_done;
+        h->pend_kind = hd.pend_kind; h->pend_depth = hd.pend_depth; h->pend_parent = hd.pend_parent; h->pend_tile = hd.pend_tile;
+        h->err = hd.err; h->pol_count = hd.pol_count; h->plies_searched = hd.plies_searched; h->pend_entry = hd.pend_entry;
+    }
+}
+
+// start mcts() for one game: fresh tree, the root position becomes the pending leaf (tentative node 0)
+__device__ __forceinline__ void kb_sp_begin(const BkState* __restrict__ states, const BkTree& tr, BkSearchHdr* hdr_g, int g,
+                                            int lane) {
+    BkRegs G;
+    bk_load(&states[g], lane, G);
+    const bool live = !bk_terminal(G) && hdr_g->err == 0u;
+    if (live) bk_store(&tr.nodes[0], lane, G);
+    if (lane == 0) {
+        hdr_g->n_nodes = 0u; hdr_g->n_entries = 0u; hdr_g->root_visits = 0u; hdr_g->sims_done = 0u;
+        hdr_g->pend_depth = 0u; hdr_g->pend_parent = 0u; hdr_g->pend_tile = 0u; hdr_g->pend_entry = 0u;
+        hdr_g->pend_kind = live ? BK_PEND_ROOT : BK_PEND_NONE;
+    }
+}
+
+// consume the evaluator's answer for the pending position, then run simulations until the next
+// non-terminal leaf needs the evaluator (or the ply's simulations are exhausted)
+__device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree& tr, BkSearchHdr* hdr_g,
+                                           const float* __restrict__ policy, const float* __restrict__ value,
+                                           unsigned long long* counters, int g, int lane, const BkTabs& tabs,
+                                           BkWarpSmem& sm) {
+    BkSearchHdr hd;
+    bk_hdr_load(hdr_g, hd, lane, sm);
+    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF) return;
+    BkCounters gctr = {0u, 0u};
+    BkSpCounters ctr = {0u, 0u, 0u, 0u};
+    const uint32_t game_id = cfg.first_game_id + uint32_t(g);
+    const float* pol = policy + size_t(g) * 400;
+    BkRegs L;
+    bk_load(&tr.nodes[hd.n_nodes], lane, L);            // the pending position (tentative node slot)
+    if (hd.pend_kind == BK_PEND_ROOT) {
+        bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr);                            // evaluate(root), value dropped
+        if (hd.n_nodes == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; }                         // reference: unwrap on None
+        else bk_tree_noise(tr, cfg, game_id, L.ply, lane);
+    } else {
+        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr);
+        if (id != BK_NODE_NONE && lane == 0) tr.TN[hd.pend_entry] = hd.pend_tile | (id << 16);
+        const int cur = bk_cur(L);
+        float val[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) val[i] = value[size_t(g) * 4 + ((i + 4 - cur) & 3)];   // value.rotate_right(cur)
+        if (lane == 0) sm.path_tp[hd.pend_depth - 1] = uint8_t(cur);
+        __syncwarp();
+        bk_tree_backup(tr, int(hd.pend_depth), val, lane, sm);
+        hd.sims_done += 1u;
+        if (lane == 0) ctr.sims += 1u;
+    }
+    hd.pend_kind = BK_PEND_DONE;
+    hd.pend_depth = 0u;
+    while (hd.sims_done < cfg.sims && hd.err == 0u) {
+        hd.root_visits += 1u;
+        const BkLeaf lf = bk_tree_select(tr, hd, cfg, lane, sm);
+        if (!lf.ok) break;
+        bk_load(&tr.nodes[lf.parent], lane, L);
+        if (!bk_apply(L, lf.tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }
+        if (lane == 0) ctr.applies += 1u;
+        if (bk_terminal(L)) {
+            float val[4];
+            bk_payoff(L, val);
+            if (lane == 0) sm.path_tp[lf.depth - 1] = 0;
+            __syncwarp();
+            bk_tree_backup(tr, lf.depth, val, lane, sm);
+            hd.sims_done += 1u;
+            if (lane == 0) ctr.sims += 1u;
+            continue;
+        }
+        if (hd.n_nodes >= cfg.max_nodes) { hd.err |= BK_SP_ERR_ENTRY_CAP; break; }
+        bk_store(&tr.nodes[hd.n_nodes], lane, L);       // tentative: becomes node n_nodes if it gets children
+        hd.pend_kind = BK_PEND_LEAF;
+        hd.pend_depth = uint32_t(lf.depth);
+        hd.pend_parent = lf.parent;
+        hd.pend_tile = uint32_t(lf.tile);
+        hd.pend_entry = lf.entry;
+        break;
+    }
+    bk_hdr_store(hdr_g, hd, lane, sm);
+    const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
+    if (lane == 0 && counters) {
+        atomicAdd(&counters[0], (unsigned long long)ctr.sims);
+        atomicAdd(&counters[1], (unsigned long long)ctr.applies);
+        atomicAdd(&counters[2], (unsigned long long)gctr.movegens);
+        atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
+        atomicAdd(&counters[4], (unsigned long long)ctr.entries);
+        atomicAdd(&counters[5], (unsigned long long)ctr.nodes);
+    }
+}
+
+// the tail of mcts() and the game.apply of training_game() for games whose simulations are done
+__device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __restrict__ states, uint16_t* __restrict__ hist,
+                                          const BkTree& tr, BkSearchHdr* hdr_g, uint32_t* pol_off, uint16_t* pol_tile,
+                                          uint32_t* pol_visits, unsigned long long* counters, int g, int lane,
+                                          const BkTabs& tabs, BkWarpSmem& sm) {
+    BkSearchHdr hd;
+    bk_hdr_load(hdr_g, hd, lane, sm);
+    if (hd.pend_kind != BK_PEND_DONE) return;
+    BkRegs G;
+    bk_load(&states[g], lane, G);
+    BkCounters gctr = {0u, 0u};
+    const uint32_t game_id = cfg.first_game_id + uint32_t(g);
+    const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
+    const int p = bk_cur(G);
+    const uint32_t ply = G.ply;
+    if (!bk_apply(G, action, -1, lane, tabs, gctr)) hd.err |= BK_SP_ERR_APPLY;
+    else {
+        if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
+        bk_store(&states[g], lane, G);
+    }
+    hd.pend_kind = BK_PEND_NONE;
+    hd.pend_depth = 0u;
+    bk_hdr_store(hdr_g, hd, lane, sm);
+    const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
+    if (lane == 0 && counters) {
+        atomicAdd(&counters[1], 1ull);
+        atomicAdd(&counters[2], (unsigned long long)gctr.movegens);
+        atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
+    }
+}

@@ -185,21 +185,28 @@ int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id);
  * evaluate/expand, backpropagate), policy record, select_action, Game::apply. */
 int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies);
 /* External-evaluator protocol, one leaf per live game per round (replaces queue.put / pipe.recv of
- * simulation.rs:50-57 by one contiguous device batch):
- *   bk_selfplay_begin_ply     : start mcts() for every live game; leaf = root.
- *   bk_selfplay_leaf_planes   : dev_planes[n_games][5][20][20] float32 of each game's pending leaf
- *                               (zeros for games with none); live_out (host, may be NULL) = number
- *                               of games with a pending leaf.
- *   bk_selfplay_expand_backup : consume dev_policy[n_games][400] (mover frame) and
- *                               dev_value[n_games][4] (relative seat), expand + backpropagate, then
- *                               run selection for the next simulation (terminal leaves are backed up
- *                               on the device without an evaluator round).
- *   bk_selfplay_end_ply       : record the policy, select_action, Game::apply.
- * sims_done_out: simulations completed in the current ply (same for every live game). */
+ * simulation.rs:50-57 by one contiguous device batch).  Per ply:
+ *   bk_selfplay_begin_ply     : start mcts() for every live game; its root position becomes the pending leaf.
+ *   loop until no game is pending:
+ *     bk_selfplay_leaf_planes   : dev_planes[n_games][5][20][20] float32 = get_board_state() of each game's
+ *                                 pending position (zeros for games with none); pending_out (host, may be NULL)
+ *                                 = number of games with a pending position.
+ *     (caller runs its evaluator on the device batch)
+ *     bk_selfplay_expand_backup : consume dev_policy[n_games][400] (mover frame) and dev_value[n_games][4]
+ *                                 (relative seat): expand the pending position (children for legal tiles with
+ *                                 policy > 0, priors exp(p)/sum), back the value up, then run further
+ *                                 simulations until each game's next NON-terminal leaf is pending (terminal
+ *                                 leaves are backed up on the device) or its sims_per_move are done.
+ *                                 pending_out (host, may be NULL) = games that now wait for the evaluator.
+ *   bk_selfplay_end_ply       : record the policy, select_action, Game::apply (BK_ERR_STATE if some game
+ *                               still has a pending position). */
 int bk_selfplay_begin_ply(bk_selfplay* sp);
-int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* live_out);
-int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* sims_done_out);
+int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending_out);
+int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* pending_out);
 int bk_selfplay_end_ply(bk_selfplay* sp);
+/* Run every kernel of this handle (and of its bk_env) on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream) so an evaluator enqueued on that stream needs no extra sync. */
+int bk_selfplay_set_stream(bk_selfplay* sp, void* cuda_stream);
 /* Number of games not yet terminal. */
 int bk_selfplay_live_games(bk_selfplay* sp, int32_t* out);
 /* The batch of games being played (borrowed; valid until bk_selfplay_destroy). */

@@ -236,3 +236,101 @@ def check_selfplay_stub(lib, orc, n_games, cfg_kwargs, first_game_id=0, max_plie
     assert ctr["sims"] == total_plies * cfg.sims_per_move
     sp.close()
     return {"plies": total_plies, "counters": ctr}
+
+
+def fixed_network(seed=0):
+    """A constant 'network': policy = table (mover frame) x legal mask (plane 4), value = fixed relative-seat
+    vector — what model/resnet.py:84-92 returns for a net that ignores its input.  Non-uniform, so selection is
+    not all ties, and the frame rotation of the policy and the rotate_right of the value both matter.  When a
+    position has two or more legal tiles the first one (mover frame) gets p == 0 and must be dropped
+    (simulation.rs:70); a position whose legal tiles all had p <= 0 would panic the reference (unwrap on None)."""
+    rng = np.random.default_rng(seed)
+    table = rng.uniform(0.05, 3.0, size=400).astype(np.float32)
+    vrel = np.array([0.4, 0.3, 0.2, 0.1], dtype=np.float32)
+
+    def one(mask400):
+        pol = (table * mask400).astype(np.float32)
+        nz = np.flatnonzero(pol)
+        if len(nz) >= 2:
+            pol[nz[0]] = 0.0
+        return pol
+
+    def batched(planes):
+        pl = np.asarray(planes)
+        n = pl.shape[0]
+        return np.stack([one(pl[i, 4].reshape(400)) for i in range(n)]), np.tile(vrel, (n, 1))
+
+    def single(_gid, planes):
+        return one(np.asarray(planes, dtype=np.float32)[4].reshape(400)), vrel
+
+    return batched, single
+
+
+def check_selfplay_evaluator(lib, orc, n_games, cfg_kwargs, first_game_id=0, max_plies=4, xp="numpy", net_seed=0):
+    """The external-evaluator protocol (begin_ply / leaf_planes / expand_backup / end_ply) with a fixed
+    non-uniform network, against the oracle driven by the same network through its evaluator callback."""
+    from blokus_self_play import SelfPlay, Config, host_evaluator
+    batched, single = fixed_network(net_seed)
+    cfg = Config(**cfg_kwargs)
+    ocfg = orc.make_config(cfg.sims_per_move, cfg.sample_moves, float(cfg.c_base), float(cfg.c_init),
+                           float(cfg.dirichlet_alpha), float(cfg.exploration_fraction), cfg.seed)
+    sp = SelfPlay(n_games, cfg, first_game_id=first_game_id, lib=lib)
+    info = sp.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, xp=xp)
+    recs = sp.policy_records()
+    hist = sp.env.history()
+    roots = sp.last_root()
+    for g in range(n_games):
+        ref = orc.selfplay_game(ocfg, first_game_id + g, max_plies=max_plies, evaluator=single)
+        assert ref["n_plies"] == len(recs[g])
+        assert [t for _, t in hist[g]] == ref["tiles"].tolist(), f"action trace differs, game {g}"
+        for k in range(ref["n_plies"]):
+            assert np.array_equal(recs[g][k][0], ref["roots"][k]["tile"]), f"children differ, game {g} ply {k}"
+            assert np.array_equal(recs[g][k][1], ref["roots"][k]["visits"]), f"visits differ, game {g} ply {k}"
+        last = ref["roots"][-1]
+        assert np.array_equal(roots[g]["prior"], last["prior"])
+        assert np.array_equal(roots[g]["value_sum"], last["value_sum"])
+    sp.close()
+    return info
+
+
+class FakeQueue:
+    """Stands in for multiprocessing.Manager().Queue + the server side of the Pipe (model/training.py:194-201):
+    put() runs the 'model' at once and the answer is handed out by recv()."""
+
+    def __init__(self, model):
+        self.model = model
+        self.answers = []
+        self.requests = 0
+
+    def put(self, item):
+        gid, planes = item
+        assert isinstance(planes, list) and len(planes) == 5 and len(planes[0]) == 20 and isinstance(planes[0][0][0], bool)
+        pol, val = self.model(gid, np.asarray(planes, dtype=np.float32))
+        self.answers.append((np.asarray(pol, dtype=np.float32).tolist(), np.asarray(val, dtype=np.float32).tolist()))
+        self.requests += 1
+
+    def recv(self):
+        return self.answers.pop(0)
+
+
+def check_play_training_game(lib, orc, cfg_kwargs, game_id=7):
+    """The reference's own entry point signature, play_training_game(id, config, inference_queue, pipe)."""
+    from blokus_self_play import play_training_game, Config
+    _, single = fixed_network(1)
+    q = FakeQueue(single)
+    cfg = Config(**cfg_kwargs)
+    history, policies, values = play_training_game(game_id, cfg, q, q, lib=lib)
+    ocfg = orc.make_config(cfg.sims_per_move, cfg.sample_moves, float(cfg.c_base), float(cfg.c_init),
+                           float(cfg.dirichlet_alpha), float(cfg.exploration_fraction), cfg.seed)
+    ref = orc.selfplay_game(ocfg, game_id, evaluator=single)
+    assert len(history) == len(policies) == ref["n_plies"]                 # simulation.rs:293-295
+    assert [t for _, t in history] == ref["tiles"].tolist() and [p for p, _ in history] == ref["players"].tolist()
+    assert values == ref["payoff"].tolist()
+    for k, pol in enumerate(policies):
+        vis = ref["roots"][k]["visits"]
+        probs = vis.astype(np.float32) / np.float32(vis.sum())
+        assert [t for t, _ in pol] == ref["roots"][k]["tile"].tolist()
+        assert np.array_equal(np.array([p for _, p in pol], dtype=np.float32), probs)
+    # one request per evaluated position: the root of every ply plus every non-terminal leaf
+    assert q.requests >= ref["n_plies"]
+    return len(history)

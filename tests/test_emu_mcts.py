@@ -13,3 +13,28 @@ def test_emu_selfplay_stub_shipped_config(emu_lib, orc):
     parity.check_selfplay_stub(emu_lib, orc, 1, dict(sims_per_move=16, sample_moves=0, c_base=19652, c_init=1.25,
                                                     dirichlet_alpha=0.3, exploration_fraction=0.25, seed=3),
                                first_game_id=0, max_plies=12)
+
+
+def test_emu_external_evaluator_protocol(emu_lib, orc):
+    info = parity.check_selfplay_evaluator(emu_lib, orc, 2, dict(sims_per_move=20, sample_moves=3, c_base=19652, c_init=1.25,
+                                                                 dirichlet_alpha=0.3, exploration_fraction=0.25, seed=9),
+                                           first_game_id=3, max_plies=5, xp="numpy")
+    assert info["plies"] == 5 and info["rounds"] >= 5 * 20
+
+
+def test_emu_external_stub_equals_fused_kernel(emu_lib, orc):
+    """The stub evaluated on the HOST through the protocol (policy 1.0 on legal tiles, value 0.25) must give
+    the fused device kernel's result bit for bit."""
+    import numpy as np
+    from blokus_self_play import SelfPlay, Config
+    kw = dict(sims_per_move=16, sample_moves=2, c_base=19652, c_init=1.25, dirichlet_alpha=0.03, exploration_fraction=0.25, seed=4)
+    a = SelfPlay(2, Config(**kw), first_game_id=1, lib=emu_lib)
+    a.run_stub(4)
+    b = SelfPlay(2, Config(**kw), first_game_id=1, lib=emu_lib)
+    b.run_evaluator(lambda pl: (pl[:, 4].reshape(-1, 400).copy(), np.full((pl.shape[0], 4), 0.25, dtype=np.float32)), 4, xp="numpy")
+    assert a.env.history() == b.env.history()
+    for ra, rb in zip(a.policy_records(), b.policy_records()):
+        for (t1, v1), (t2, v2) in zip(ra, rb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    for x, y in zip(a.last_root(), b.last_root()):
+        assert np.array_equal(x["prior"], y["prior"]) and np.array_equal(x["value_sum"], y["value_sum"])

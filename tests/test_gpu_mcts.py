@@ -66,3 +66,32 @@ def test_gpu_selfplay_1024_games_invariants(cuda_lib, orc):
         for (t1, v1), (t2, v2) in zip(rs[g], recs[512 + g]):
             assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
     assert shard.env.history() == sp.env.history()[512:768]
+
+
+def test_gpu_external_evaluator_protocol(cuda_lib, orc):
+    """Non-uniform fixed network through begin_ply / leaf_planes / expand_backup / end_ply (device batches)."""
+    info = parity.check_selfplay_evaluator(cuda_lib, orc, 8, dict(CONFIG3, sims_per_move=96, dirichlet_alpha=0.3, seed=2),
+                                           first_game_id=40, max_plies=12, xp="torch")
+    assert info["plies"] == 12
+
+
+def test_gpu_play_training_game_reference_signature(cuda_lib, orc):
+    """play_training_game(id, config, inference_queue, pipe) — the reference's entry point and IPC protocol
+    (self_play/src/lib.rs:9-32, simulation.rs:50-57), a whole game, tuple shape of simulation.rs:293-295."""
+    n = parity.check_play_training_game(cuda_lib, orc, dict(sims_per_move=12, sample_moves=30, c_base=19652, c_init=1.25,
+                                                            dirichlet_alpha=0.3, exploration_fraction=0.25, seed=6))
+    assert n > 200
+
+
+def test_gpu_external_stub_equals_fused_kernel(cuda_lib, orc):
+    import torch
+    from blokus_self_play import SelfPlay, Config
+    kw = dict(CONFIG3, sims_per_move=200)
+    a = SelfPlay(32, Config(**kw), first_game_id=9, lib=cuda_lib)
+    a.run_stub(6)
+    b = SelfPlay(32, Config(**kw), first_game_id=9, lib=cuda_lib)
+    b.run_evaluator(lambda pl: (pl[:, 4].reshape(-1, 400), torch.full((pl.shape[0], 4), 0.25, device=pl.device)), 6)
+    assert a.env.history() == b.env.history()
+    for ra, rb in zip(a.policy_records(), b.policy_records()):
+        for (t1, v1), (t2, v2) in zip(ra, rb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)

@@ -1,0 +1,76 @@
+"""The leaf evaluator (blokus_self_play/resnet.py) against golden vectors produced by the reference's own
+model/resnet.py (tests/golden/make_resnet_golden.py, run in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet_2x16.npz")
+
+
+def load_model():
+    from blokus_self_play.resnet import ResNet
+    z = np.load(GOLD)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model = ResNet(2, 16)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return model.eval(), z
+
+
+def test_state_dict_names_match_reference():
+    model, z = load_model()
+    assert sorted(model.state_dict().keys()) == sorted(k[3:] for k in z.files if k.startswith("sd/"))
+    assert sum(p.numel() for p in model.parameters()) + sum(b.numel() for b in model.buffers()) == 11924
+
+
+def test_forward_matches_reference_cpu_fp32():
+    model, z = load_model()
+    with torch.no_grad():
+        policy, value = model(torch.from_numpy(z["planes"]))
+    # fp32 on the same CPU kernels: tolerance 1e-6 absolute (softmax outputs in [0, 1])
+    assert np.allclose(policy.numpy(), z["policy"], atol=1e-6, rtol=0)
+    assert np.allclose(value.numpy(), z["value"], atol=1e-6, rtol=0)
+    mask = z["planes"][:, 4].reshape(len(z["planes"]), -1)
+    assert np.all(policy.numpy()[mask == 0] == 0)                      # resnet.py:88 — zero on illegal tiles
+    assert np.allclose(policy.numpy().sum(axis=1), 1.0, atol=1e-5)
+    assert np.allclose(value.numpy().sum(axis=1), 1.0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_forward_matches_reference_on_gpu():
+    from blokus_self_play.resnet import LeafEvaluator
+    model, z = load_model()
+    x = torch.from_numpy(z["planes"]).cuda()
+    p, v = LeafEvaluator(model.cuda())(x)
+    # fp32 cuDNN vs the CPU golden: 1e-5 absolute
+    assert np.allclose(p.cpu().numpy(), z["policy"], atol=1e-5, rtol=0)
+    assert np.allclose(v.cpu().numpy(), z["value"], atol=1e-5, rtol=0)
+    pb, vb = LeafEvaluator(model.cuda(), bf16=True)(x)
+    # bf16 autocast (config 4's compute dtype): 8 mantissa bits through 5 conv layers -> 3e-2 absolute
+    assert np.allclose(pb.cpu().numpy(), z["policy"], atol=3e-2, rtol=0)
+    assert np.allclose(vb.cpu().numpy(), z["value"], atol=3e-2, rtol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_selfplay_with_resnet_config4_shape(cuda_lib, orc):
+    """BASELINE.json config 4 in miniature: batched leaf evaluation on a random-init ResNet through the
+    external-evaluator protocol.  Visit parity with an fp32 CPU model is not defined; the tree
+    invariants are: every ply's root visits sum to sims_per_move, children ascending, every game advances."""
+    from blokus_self_play import SelfPlay, Config
+    from blokus_self_play.resnet import ResNet, LeafEvaluator
+    torch.manual_seed(7)
+    ev = LeafEvaluator(ResNet(4, 32).cuda())
+    cfg = Config(sims_per_move=48, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                 exploration_fraction=0.25, seed=3)
+    sp = SelfPlay(64, cfg, lib=cuda_lib)
+    info = sp.run_evaluator(ev, max_plies=6)
+    assert info["plies"] == 6
+    for recs in sp.policy_records():
+        assert len(recs) == 6
+        for tiles, visits in recs:
+            assert int(visits.sum()) == 48 and np.all(np.diff(tiles) > 0)
+    assert all(len(h) == 6 for h in sp.env.history())
+    c = sp.counters()
+    assert c["sims"] == 64 * 6 * 48
