@@ -45,7 +45,7 @@ k_place_piece(BkState* __restrict__ states, uint16_t* __restrict__ hist, const i
 }
 
 // One warp per CTA: the hardware CTA scheduler balances games of different length over the SMs.
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 28)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
           const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
           unsigned long long* counters) {

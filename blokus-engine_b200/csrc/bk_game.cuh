@@ -166,10 +166,41 @@ struct BkNarrow {
     bool any_valid;  // some turn-start placement contains T (always true after a legal tile)
 };
 
+// Survivors of the current turn's narrowing, carried in registers by kernels that apply several tiles
+// in a row (the persistent playout).  Stateless callers pass a fresh cache every time.
+struct BkTurnCache {
+    uint32_t smask;      // lane-local: bit ch set iff candidate ch*32+lane is still consistent
+    uint32_t alive;      // warp-uniform: chunks with at least one survivor
+    uint32_t tw0, tw1, tw2;  // window mask of the tiles laid this turn
+    int valid_ply;       // history length the cache belongs to; -1 = nothing cached
+};
+__device__ __forceinline__ BkTurnCache bk_no_cache() {
+    BkTurnCache c;
+    c.smask = 0u; c.alive = 0u; c.tw0 = c.tw1 = c.tw2 = 0u; c.valid_ply = -1;
+    return c;
+}
+
+// window word index / bit of board tile t relative to the window centred on (tr, tc)
+__device__ __forceinline__ void bk_window_bit(int t, int tr, int tc, int& k, uint32_t& b) {
+    const int bit = (t / 20 - tr + 4) * 9 + (t % 20 - tc + 4);
+    k = bit / 27;
+    b = 1u << (bit - 27 * k);
+}
+
+// scatter the 9x9 window legal mask back to this lane's board row
+__device__ __forceinline__ uint32_t bk_window_to_row(uint32_t L0, uint32_t L1, uint32_t L2, int tr, int tc, int lane) {
+    const int wr = lane - tr + 4;
+    if (wr < 0 || wr >= 9 || lane >= 20) return 0u;
+    const int wk = wr / 3;
+    const uint32_t Lw = wk == 0 ? L0 : (wk == 1 ? L1 : L2);
+    const uint32_t slice = (Lw >> (9 * (wr - 3 * wk))) & 0x1FFu;
+    return ((slice << tc) >> 4) & BK_ROWMASK;
+}
+
 // S = { turn-start-valid placements containing all nT tiles in T }, evaluated inside the 9x9 window
-// centred on T[0].  free_/anch are the TURN-START rows of this lane.
-__device__ __forceinline__ BkNarrow bk_narrow(uint32_t free_, uint32_t anch, uint32_t pieces, const int (&T)[5],
-                                              int nT, int lane, const BkTabs& tabs) {
+// centred on T[0].  free_/anch are the TURN-START rows of this lane.  Fills `cache` with the survivors.
+__device__ __forceinline__ BkNarrow bk_narrow_full(uint32_t free_, uint32_t anch, uint32_t pieces, const int (&T)[5],
+                                                   int nT, int lane, const BkTabs& tabs, BkTurnCache& cache) {
     const int tr = T[0] / 20, tc = T[0] % 20;
     const uint32_t fs = ((free_ << 4) >> tc) & 0x1FFu;
     const uint32_t as = ((anch << 4) >> tc) & 0x1FFu;
@@ -183,48 +214,102 @@ __device__ __forceinline__ BkNarrow bk_narrow(uint32_t free_, uint32_t anch, uin
     const uint32_t AW0 = __reduce_or_sync(BK_FULL, wk == 0 ? as << sh : 0u);
     const uint32_t AW1 = __reduce_or_sync(BK_FULL, wk == 1 ? as << sh : 0u);
     const uint32_t AW2 = __reduce_or_sync(BK_FULL, wk == 2 ? as << sh : 0u);
-    uint32_t TW0 = 0u, TW1 = 0u, TW2 = 0u;
+    uint32_t TW0 = 0u, TW1 = 1u << 13, TW2 = 0u;   // T[0] is the window centre: bit 4*9+4 = 40 = word 1, bit 13
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 1; i < 5; ++i) {
         if (i < nT) {
-            const int r = T[i] / 20 - tr + 4, c = T[i] % 20 - tc + 4;
-            const int bit = r * 9 + c;
-            const int k = bit / 27;
-            const uint32_t b = 1u << (bit - 27 * k);
+            int k; uint32_t b;
+            bk_window_bit(T[i], tr, tc, k, b);
             if (k == 0) TW0 |= b; else if (k == 1) TW1 |= b; else TW2 |= b;
         }
     }
-    uint32_t L0 = 0u, L1 = 0u, L2 = 0u;
+    uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = 0u;
     int found = 0;
+    if (nT == 1) {
+        // first tile of the turn: every candidate contains T by construction — no "covers" test
 #pragma unroll 1
-    for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
-        if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
-        const int idx = ch * 32 + lane;
-        const uint32_t w0 = tabs.w0[idx];
-        const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
-        const uint32_t pid = w0 >> 27;
-        const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
-        const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
-        const bool covers = (((m0 & TW0) ^ TW0) | ((m1 & TW1) ^ TW1) | ((m2 & TW2) ^ TW2)) == 0u;
-        if (((pieces >> pid) & 1u) && fits && hits && covers) {
-            L0 |= m0; L1 |= m1; L2 |= m2;
-            found = int(pid) + 1;
+        for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
+            if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
+            const int idx = ch * 32 + lane;
+            const uint32_t w0 = tabs.w0[idx];
+            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
+            const uint32_t pid = w0 >> 27;
+            const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
+            const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
+            if (((pieces >> pid) & 1u) && fits && hits) {
+                L0 |= m0; L1 |= m1; L2 |= m2;
+                found = int(pid) + 1;
+                smask |= 1u << ch;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
+            if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
+            const int idx = ch * 32 + lane;
+            const uint32_t w0 = tabs.w0[idx];
+            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
+            const uint32_t pid = w0 >> 27;
+            const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
+            const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
+            const bool covers = (((m0 & TW0) ^ TW0) | ((m1 & TW1) ^ TW1) | ((m2 & TW2) ^ TW2)) == 0u;
+            if (((pieces >> pid) & 1u) && fits && hits && covers) {
+                L0 |= m0; L1 |= m1; L2 |= m2;
+                found = int(pid) + 1;
+                smask |= 1u << ch;
+            }
         }
     }
     L0 = __reduce_or_sync(BK_FULL, L0) & ~TW0;
     L1 = __reduce_or_sync(BK_FULL, L1) & ~TW1;
     L2 = __reduce_or_sync(BK_FULL, L2) & ~TW2;
     found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+    cache.smask = smask;
+    cache.alive = __reduce_or_sync(BK_FULL, smask);
+    cache.tw0 = TW0; cache.tw1 = TW1; cache.tw2 = TW2;
     BkNarrow out;
     out.pid = found - 1;
     out.any_valid = found > 0;
-    uint32_t row = 0u;
-    if (inw) {
-        const uint32_t Lw = wk == 0 ? L0 : (wk == 1 ? L1 : L2);
-        const uint32_t slice = (Lw >> sh) & 0x1FFu;
-        row = ((slice << tc) >> 4) & BK_ROWMASK;
+    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    return out;
+}
+
+// Second and later tiles of a turn when the previous tile's survivors are cached: S only shrinks
+// (game.rs:165-173 intersects with the placements through the new tile), so only survivors are
+// re-tested, and only against the new tile.
+__device__ __forceinline__ BkNarrow bk_narrow_incr(const int (&T)[5], int nT, int lane, const BkTabs& tabs,
+                                                   BkTurnCache& cache) {
+    const int tr = T[0] / 20, tc = T[0] % 20;
+    int k; uint32_t b;
+    bk_window_bit(T[nT - 1], tr, tc, k, b);
+    if (k == 0) cache.tw0 |= b; else if (k == 1) cache.tw1 |= b; else cache.tw2 |= b;
+    uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = cache.smask;
+    int found = 0;
+    for (uint32_t cm = cache.alive; cm; cm &= cm - 1u) {   // warp-uniform
+        const int ch = __ffs(cm) - 1;
+        if ((smask >> ch) & 1u) {
+            const int idx = ch * 32 + lane;
+            const uint32_t w0 = tabs.w0[idx];
+            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
+            const uint32_t mk = k == 0 ? m0 : (k == 1 ? m1 : m2);
+            if (mk & b) {
+                L0 |= m0; L1 |= m1; L2 |= m2;
+                found = int(w0 >> 27) + 1;
+            } else {
+                smask &= ~(1u << ch);
+            }
+        }
     }
-    out.legal = row;
+    L0 = __reduce_or_sync(BK_FULL, L0) & ~cache.tw0;
+    L1 = __reduce_or_sync(BK_FULL, L1) & ~cache.tw1;
+    L2 = __reduce_or_sync(BK_FULL, L2) & ~cache.tw2;
+    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+    cache.smask = smask;
+    cache.alive = __reduce_or_sync(BK_FULL, smask);
+    BkNarrow out;
+    out.pid = found - 1;
+    out.any_valid = found > 0;
+    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
     return out;
 }
 
@@ -244,9 +329,21 @@ __device__ __forceinline__ uint32_t bk_T_row(const int (&T)[5], int nT, int lane
     return m;
 }
 
+// position of the k-th (0-based) set bit of a word whose live bits are below bit 32; branch-free
+// binary search on popcounts (the __fns intrinsic is a long software loop)
+__device__ __forceinline__ int bk_kth_set_bit(uint32_t m, int k) {
+    int pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = int(m & 1u);         if (k >= c) { pos += 1; }
+    return pos;
+}
+
 __device__ __forceinline__ int bk_nth_set_bit(uint32_t mask, int n) {  // n-th (0-based) set bit, -1 if none
     if (n < 0 || n >= __popc(mask)) return -1;
-    return int(__fns(mask, 0u, n + 1));
+    return bk_kth_set_bit(mask, n);
 }
 
 // Game::advance_player (game.rs:203-223) as a loop: next seat that is not eliminated and has a
@@ -273,7 +370,15 @@ __device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr)
 // Game::apply(tile, piece_to_finish) (game.rs:150-194).  finish < 0 is None.  Returns false (and
 // leaves the game untouched) when the tile is not legal or finish is out of range.
 __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
+                                         BkCounters& ctr, BkTurnCache& cache);
+// stateless form: narrow from scratch
+__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
                                          BkCounters& ctr) {
+    BkTurnCache cache = bk_no_cache();
+    return bk_apply(G, tile, finish, lane, tabs, ctr, cache);
+}
+__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
+                                         BkCounters& ctr, BkTurnCache& cache) {
     if (tile < 0 || tile >= 400 || bk_terminal(G)) return false;
     const int p = bk_cur(G);
     const int tr = tile / 20, tc = tile % 20;
@@ -293,12 +398,17 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
     // derived from the bitboards on demand.
     if (p == 0) G.o0 |= bit; else if (p == 1) G.o1 |= bit; else if (p == 2) G.o2 |= bit; else G.o3 |= bit;
     G.ply += 1u;
-    const uint32_t trow = bk_T_row(T, nT, lane);
-    const uint32_t mine0 = bk_sel4(p, G.o0, G.o1, G.o2, G.o3) & ~trow;
-    const uint32_t occ0 = (G.o0 | G.o1 | G.o2 | G.o3) & ~trow;
-    uint32_t free_, anch;
-    bk_free_anchor(mine0, occ0, p, lane, free_, anch);
-    const BkNarrow nw = bk_narrow(free_, anch, pieces, T, nT, lane, tabs);
+    BkNarrow nw;
+    if (nT > 1 && cache.valid_ply == int(G.ply) - 1) {
+        nw = bk_narrow_incr(T, nT, lane, tabs, cache);
+    } else {
+        const uint32_t trow = bk_T_row(T, nT, lane);
+        const uint32_t mine0 = bk_sel4(p, G.o0, G.o1, G.o2, G.o3) & ~trow;
+        const uint32_t occ0 = (G.o0 | G.o1 | G.o2 | G.o3) & ~trow;
+        uint32_t free_, anch;
+        bk_free_anchor(mine0, occ0, p, lane, free_, anch);
+        nw = bk_narrow_full(free_, anch, pieces, T, nT, lane, tabs, cache);
+    }
     const bool done = !__any_sync(BK_FULL, nw.legal != 0u);
     if (done || fin_pid >= 0) {
         // game.rs:176-191: commit the piece, remember its size, pass the turn
@@ -309,8 +419,10 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
         G.lastlens = (G.lastlens & ~(0xFFu << (8 * p))) | (len << (8 * p));
         G.meta &= ~(7u << 6);
         G.t01 = 0u; G.t23 = 0u;
+        cache.valid_ply = -1;
         bk_advance(G, lane, ctr);
     } else {
+        cache.valid_ply = int(G.ply);
         G.legal = nw.legal;
         G.meta = (G.meta & ~(7u << 6)) | (uint32_t(nT) << 6);
         G.t01 = uint32_t(T[0]) | (uint32_t(T[1]) << 16);
@@ -404,7 +516,7 @@ __device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane
     const int excl = incl - cnt;
     const bool here = (idx >= excl) && (idx < incl);
     int tile = 0;
-    if (here) tile = lane * 20 + int(__fns(legal, 0u, idx - excl + 1));
+    if (here) tile = lane * 20 + bk_kth_set_bit(legal, idx - excl);
     const unsigned who = __ballot_sync(BK_FULL, here);
     return __shfl_sync(BK_FULL, tile, who ? (__ffs(who) - 1) : 0);
 }

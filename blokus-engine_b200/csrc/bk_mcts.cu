@@ -16,10 +16,8 @@ struct bk_selfplay {
     uint32_t first_id = 0;
     bk_env* env = nullptr;
     BkSearchCfg dcfg{};
-    uint32_t* d_N = nullptr;
-    float* d_W = nullptr;
-    float* d_P = nullptr;
-    uint32_t* d_TN = nullptr;
+    uint4* d_S = nullptr;
+    uint4* d_X = nullptr;
     BkState* d_nodes = nullptr;
     double* d_scratch = nullptr;
     BkSearchHdr* d_hdr = nullptr;
@@ -36,14 +34,14 @@ struct bk_selfplay {
 
 // ---- kernels ------------------------------------------------------------------------------------------
 struct BkPools {
-    uint32_t* N; float* W; float* P; uint32_t* TN; BkState* nodes; double* scratch; BkSearchHdr* hdr;
+    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr;
     uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
 };
 
 __device__ __forceinline__ BkTree bk_tree_of(const BkPools& pl, const BkSearchCfg& cfg, int g) {
     BkTree t;
     const size_t eo = size_t(g) * cfg.entry_cap;
-    t.N = pl.N + eo; t.W = pl.W + eo; t.P = pl.P + eo; t.TN = pl.TN + eo;
+    t.S = pl.S + eo; t.X = pl.X + eo;
     t.nodes = pl.nodes + size_t(g) * cfg.max_nodes;
     t.scratch = pl.scratch + size_t(g) * 400;
     return t;
@@ -133,10 +131,11 @@ __global__ void k_last_root(BkSearchCfg cfg, BkPools pl, int n, int32_t* counts,
     if (threadIdx.x == 0) counts[g] = cnt;
     for (int i = threadIdx.x; i < 400; i += blockDim.x) {
         const bool in = i < cnt;
-        tile[size_t(g) * 400 + i] = in ? int16_t(tr.TN[off + i] & 0xFFFFu) : int16_t(-1);
-        visits[size_t(g) * 400 + i] = in ? tr.N[off + i] : 0u;
-        wsum[size_t(g) * 400 + i] = in ? tr.W[off + i] : 0.0f;
-        prior[size_t(g) * 400 + i] = in ? tr.P[off + i] : 0.0f;
+        const uint4 sv = in ? tr.S[off + i] : make_uint4(0u, 0u, 0u, 0u);
+        tile[size_t(g) * 400 + i] = in ? int16_t(BK_TN_TILE(sv.w)) : int16_t(-1);
+        visits[size_t(g) * 400 + i] = sv.x;
+        wsum[size_t(g) * 400 + i] = in ? __uint_as_float(tr.X[off + i].x) : 0.0f;
+        prior[size_t(g) * 400 + i] = __uint_as_float(sv.z);
     }
 }
 
@@ -145,7 +144,7 @@ static float host_exp_f32(float x) { return float(std::exp(double(x))); }  // sa
 
 static BkPools pools_of(const bk_selfplay* sp) {
     BkPools p;
-    p.N = sp->d_N; p.W = sp->d_W; p.P = sp->d_P; p.TN = sp->d_TN; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
+    p.S = sp->d_S; p.X = sp->d_X; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
     p.hdr = sp->d_hdr; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
     return p;
 }
@@ -177,8 +176,8 @@ extern "C" {
 int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t first_game_id,
                        uint32_t max_children_per_game, bk_selfplay** out) {
     if (!cfg || !out || n_games <= 0) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: bad argument");
-    if (cfg->sims_per_move == 0 || cfg->sims_per_move > 65000u)
-        return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: sims_per_move must be in 1..65000");
+    if (cfg->sims_per_move == 0 || cfg->sims_per_move > 1000000u)
+        return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: sims_per_move must be in 1..1000000");
     if (!(cfg->c_base > 0.0f)) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: c_base must be > 0");
     if (!(cfg->dirichlet_alpha > 0.0f)) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_create: dirichlet_alpha must be > 0");
     bk_selfplay* sp = new bk_selfplay();
@@ -200,10 +199,8 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     d.policy_cap = 32768u;
     d.stub_value = 0.25f;
     const size_t ne = size_t(n_games) * d.entry_cap;
-    BK_CUDA(cudaMalloc(&sp->d_N, sizeof(uint32_t) * ne));
-    BK_CUDA(cudaMalloc(&sp->d_W, sizeof(float) * ne));
-    BK_CUDA(cudaMalloc(&sp->d_P, sizeof(float) * ne));
-    BK_CUDA(cudaMalloc(&sp->d_TN, sizeof(uint32_t) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_S, sizeof(uint4) * ne));
+    BK_CUDA(cudaMalloc(&sp->d_X, sizeof(uint4) * ne));
     BK_CUDA(cudaMalloc(&sp->d_nodes, sizeof(BkState) * size_t(n_games) * d.max_nodes));
     BK_CUDA(cudaMalloc(&sp->d_scratch, sizeof(double) * 400 * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_hdr, sizeof(BkSearchHdr) * size_t(n_games)));
@@ -242,7 +239,7 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
 void bk_selfplay_destroy(bk_selfplay* sp) {
     if (!sp) return;
     cudaSetDevice(sp->device);
-    cudaFree(sp->d_N); cudaFree(sp->d_W); cudaFree(sp->d_P); cudaFree(sp->d_TN); cudaFree(sp->d_nodes);
+    cudaFree(sp->d_S); cudaFree(sp->d_X); cudaFree(sp->d_nodes);
     cudaFree(sp->d_scratch); cudaFree(sp->d_hdr); cudaFree(sp->d_pol_off); cudaFree(sp->d_pol_tile);
     cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
     cudaFree(sp->d_stage);

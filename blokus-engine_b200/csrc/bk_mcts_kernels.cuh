@@ -4,9 +4,14 @@
 // Tree layout (per game, in HBM).  A reference `Node` is one CHILD ENTRY of its parent; entries of one
 // parent are contiguous and in ascending tile order (the canonical stand-in for HashMap iteration,
 // SURVEY.md Appendix D):
-//     N[cap] u32 visits | W[cap] f32 value_sum | P[cap] f32 prior | TN[cap] u32 = tile | node << 16
-// (struct of arrays: lane i of a select reads N[off+i], W[off+i], P[off+i] — three coalesced loads).
-// An entry that has been expanded points (node) into the node table, whose records are full game states
+//     S[cap] = { N u32 visits, Q f32 = value_sum/visits (0 if unvisited), P f32 prior,
+//                TN u32 = tile | n_children << 9 | to_play << 18 | expanded << 20 }      (select stream)
+//     X[cap] = { W f32 value_sum, child block offset u32, node id u32, - }               (backup / descent stream)
+// two coalesced 16-byte vector streams: lane i of a select issues S[off+i] and X[off+i] together, so one
+// tree level costs ONE dependent memory round trip (the winner's child block offset, size, seat and node
+// id arrive with its statistics; nothing is chased through the node table).  Q is refreshed by the backup,
+// which removes one IEEE division per child per select.
+// An entry that has been expanded points (node id) into the node table, whose records are full game states
 // (BkState) plus the child block offset/count.  Keeping the state of every expanded node in HBM replaces
 // the reference's "clone the game and replay the path" (simulation.rs:196-203) by ONE Game::apply per
 // simulation — same states, same results, depth-times less rules work; 180 GB of HBM pays for it.
@@ -19,7 +24,11 @@
 #include "bk_env_kernels.cuh"
 
 #define BK_PATH_CAP 128
-#define BK_NODE_NONE 0xFFFFu
+#define BK_NODE_NONE 0xFFFFFFFFu
+#define BK_TN_TILE(tn) ((tn) & 0x1FFu)
+#define BK_TN_NCHILD(tn) (((tn) >> 9) & 0x1FFu)
+#define BK_TN_TOPLAY(tn) (((tn) >> 18) & 3u)
+#define BK_TN_EXPANDED(tn) (((tn) >> 20) & 1u)
 
 #define BK_SP_ERR_ENTRY_CAP 1u
 #define BK_SP_ERR_PATH_CAP 2u
@@ -39,10 +48,8 @@ struct BkSearchCfg {
 };
 
 struct BkTree {
-    uint32_t* N;
-    float* W;
-    float* P;
-    uint32_t* TN;
+    uint4* S;         // [entry_cap] {N, Q, P, TN}
+    uint4* X;         // [entry_cap] {W, child_off, node id, -}
     BkState* nodes;   // [max_nodes]; pad[0] = child offset, pad[1] = child count
     double* scratch;  // [400]
 };
@@ -137,11 +144,11 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
     }
     const uint32_t off = hd.n_entries;
     const uint32_t id = hd.n_nodes;
+    const float stub_prior = cfg.prior_tab[n];
     for (int i = lane; i < n; i += 32) {
-        tr.N[off + i] = 0u;
-        tr.W[off + i] = 0.0f;
-        tr.P[off + i] = policy ? __fdiv_rn(sm.e[i], total) : cfg.prior_tab[n];
-        tr.TN[off + i] = uint32_t(sm.tile[i]) | (BK_NODE_NONE << 16);
+        const float pr = policy ? __fdiv_rn(sm.e[i], total) : stub_prior;
+        tr.S[off + i] = make_uint4(0u, 0u, __float_as_uint(pr), uint32_t(sm.tile[i]));
+        tr.X[off + i] = make_uint4(0u, 0u, BK_NODE_NONE, 0u);
     }
     BkState* ns = &tr.nodes[id];
     bk_store(ns, lane, L);
@@ -151,6 +158,23 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
     if (lane == 0) { ctr.entries += uint32_t(n); ctr.nodes += 1u; }
     __syncwarp();
     return id;
+}
+
+// after evaluate(): the leaf entry remembers the seat to move at it (node.to_play, simulation.rs:78) and,
+// if it got children, its child block and node id
+__device__ __forceinline__ void bk_tree_link(const BkTree& tr, uint32_t entry, int tile, uint32_t id, int to_play,
+                                             int lane) {
+    if (lane == 0) {
+        uint32_t tn = uint32_t(tile) | (uint32_t(to_play) << 18);
+        if (id != BK_NODE_NONE) {
+            const BkState* ns = &tr.nodes[id];
+            tn |= (ns->pad[1] << 9) | (1u << 20);
+            tr.X[entry].y = ns->pad[0];
+            tr.X[entry].z = id;
+        }
+        tr.S[entry].w = tn;
+    }
+    __syncwarp();
 }
 
 // add_exploration_noise (simulation.rs:101-114) on the root's child block
@@ -177,7 +201,8 @@ __device__ __forceinline__ void bk_tree_noise(const BkTree& tr, const BkSearchCf
     const float keepf = __fsub_rn(1.0f, cfg.frac);
     for (int i = lane; i < n; i += 32) {
         const float noise = float(__ddiv_rn(tr.scratch[i], sum));
-        tr.P[off + i] = __fadd_rn(__fmul_rn(tr.P[off + i], keepf), __fmul_rn(noise, cfg.frac));
+        const float pr = __uint_as_float(tr.S[off + i].z);
+        tr.S[off + i].z = __float_as_uint(__fadd_rn(__fmul_rn(pr, keepf), __fmul_rn(noise, cfg.frac)));
     }
     __syncwarp();
 }
@@ -195,45 +220,45 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
                                                  BkWarpSmem& sm) {
     BkLeaf lf;
     lf.ok = true;
+    lf.parent = 0u; lf.entry = 0u; lf.tile = 0;
     uint32_t node = 0u;
+    uint32_t off = tr.nodes[0].pad[0];
+    int n = int(tr.nodes[0].pad[1]);
     uint32_t Np = hd.root_visits;
     int depth = 0;
     for (;;) {
-        const BkState* ns = &tr.nodes[node];
-        const uint32_t off = ns->pad[0];
-        const int n = int(ns->pad[1]);
         const float F = cfg.ucb_tab[Np];
         float best = 0.0f;
         int bi = -1;
+        uint32_t b_tn = 0u, b_n = 0u, b_off = 0u, b_node = 0u;
         for (int i = lane; i < n; i += 32) {
-            const uint32_t nc = tr.N[off + i];
-            const float w = tr.W[off + i];
-            const float pr = tr.P[off + i];
-            const float fn = float(nc);
-            const float q = nc ? __fdiv_rn(w, fn) : 0.0f;                       // node.rs:33-39
-            const float u = __fdiv_rn(F, __fadd_rn(1.0f, fn));                  // simulation.rs:92-94
-            const float sc = __fadd_rn(__fmul_rn(u, pr), q);                    // simulation.rs:95-97
-            if (sc >= best) { best = sc; bi = i; }                              // simulation.rs:141
+            const uint4 sv = tr.S[off + i];
+            const uint4 xv = tr.X[off + i];
+            const float q = __uint_as_float(sv.y);                              // node.rs:33-39 (kept by backup)
+            const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));         // simulation.rs:92-94
+            const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), q); // simulation.rs:95-97
+            if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z; }  // :141
         }
         const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
         const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
         if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
         const uint32_t wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
-        const uint32_t e = off + wi;
-        const uint32_t tn = tr.TN[e];
+        const int src = int(wi & 31u);                     // child i lives on lane i % 32
+        const uint32_t tn = __shfl_sync(BK_FULL, b_tn, src);
         if (depth >= BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; break; }
-        const uint32_t child = tn >> 16;
-        if (lane == 0) sm.path[depth] = e;
+        const uint32_t e = off + wi;
+        if (lane == 0) { sm.path[depth] = e; sm.path_tp[depth] = uint8_t(BK_TN_TOPLAY(tn)); }
         ++depth;
-        if (child == BK_NODE_NONE) {
+        if (!BK_TN_EXPANDED(tn)) {
             lf.parent = node;
             lf.entry = e;
-            lf.tile = int(tn & 0xFFFFu);
+            lf.tile = int(BK_TN_TILE(tn));
             break;
         }
-        if (lane == 0) sm.path_tp[depth - 1] = uint8_t(tr.nodes[child].meta & 3u);
-        Np = tr.N[e];
-        node = child;
+        Np = __shfl_sync(BK_FULL, b_n, src);
+        off = __shfl_sync(BK_FULL, b_off, src);
+        node = __shfl_sync(BK_FULL, b_node, src);
+        n = int(BK_TN_NCHILD(tn));
     }
     lf.depth = depth;
     __syncwarp();
@@ -247,8 +272,10 @@ __device__ __forceinline__ void bk_tree_backup(const BkTree& tr, int depth, cons
     for (int d = lane; d < depth; d += 32) {
         const uint32_t e = sm.path[d];
         const int tp = int(sm.path_tp[d]);
-        tr.N[e] += 1u;
-        tr.W[e] = __fadd_rn(tr.W[e], bk_sel4f(tp, val[0], val[1], val[2], val[3]));
+        const uint32_t nv = tr.S[e].x + 1u;                                                          // visits += 1
+        const float w = __fadd_rn(__uint_as_float(tr.X[e].x), bk_sel4f(tp, val[0], val[1], val[2], val[3]));
+        tr.X[e].x = __float_as_uint(w);                                                              // value_sum +=
+        *reinterpret_cast<uint2*>(&tr.S[e]) = make_uint2(nv, __float_as_uint(__fdiv_rn(w, float(nv))));  // N, Q
     }
     __syncwarp();
 }
@@ -266,8 +293,9 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
         hd.err |= BK_SP_ERR_POLICY_CAP;
     } else {
         for (int i = lane; i < n; i += 32) {
-            pol_tile[hd.pol_count + i] = uint16_t(tr.TN[off + i] & 0xFFFFu);
-            pol_visits[hd.pol_count + i] = tr.N[off + i];
+            const uint4 sv = tr.S[off + i];
+            pol_tile[hd.pol_count + i] = uint16_t(BK_TN_TILE(sv.w));
+            pol_visits[hd.pol_count + i] = sv.x;
         }
         if (lane == 0) { pol_off[k] = hd.pol_count; pol_off[k + 1] = hd.pol_count + uint32_t(n); }
         hd.pol_count += uint32_t(n);
@@ -276,13 +304,13 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
     int pick = -1;
     if (hd.plies_searched < cfg.sample_moves) {
         uint32_t total = 0u;
-        for (int i = lane; i < n; i += 32) total += tr.N[off + i];
+        for (int i = lane; i < n; i += 32) total += tr.S[off + i].x;
         total = __reduce_add_sync(BK_FULL, total);
         const float u = bk_action_uniform(cfg.seed, game_id, ply);
         const float ft = float(total);
         float sum = 0.0f;
         for (int i = 0; i < n; ++i) {                                            // simulation.rs:123-128
-            sum = __fadd_rn(sum, __fdiv_rn(float(tr.N[off + i]), ft));
+            sum = __fadd_rn(sum, __fdiv_rn(float(tr.S[off + i].x), ft));
             if (sum > u) { pick = i; break; }
         }
         if (pick < 0) pick = n - 1;                                              // simulation.rs:129
@@ -290,14 +318,14 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
         uint32_t bestv = 0u;
         int bi = -1;
         for (int i = lane; i < n; i += 32) {
-            const uint32_t v = tr.N[off + i];
+            const uint32_t v = tr.S[off + i].x;
             if (v >= bestv) { bestv = v; bi = i; }                               // max_by keeps the last maximum
         }
         const uint32_t key = bi >= 0 ? bestv + 1u : 0u;
         const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
         pick = int(__reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u)) - 1;
     }
-    return int(tr.TN[off + uint32_t(pick)] & 0xFFFFu);
+    return int(BK_TN_TILE(tr.S[off + uint32_t(pick)].w));
 }
 
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
@@ -317,8 +345,8 @@ __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, c
         bk_payoff(L, val);                                                       // simulation.rs:45-47
     } else {
         const uint32_t id = bk_tree_expand(tr, hd, cfg, L, nullptr, lane, sm, ctr);
-        if (id != BK_NODE_NONE && lane == 0) tr.TN[lf.entry] = uint32_t(lf.tile) | (id << 16);
         tp = bk_cur(L);                                                          // simulation.rs:78
+        bk_tree_link(tr, lf.entry, lf.tile, id, tp, lane);
         val[0] = val[1] = val[2] = val[3] = cfg.stub_value;
     }
     if (lane == 0) sm.path_tp[lf.depth - 1] = uint8_t(tp);
@@ -439,8 +467,8 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
         else bk_tree_noise(tr, cfg, game_id, L.ply, lane);
     } else {
         const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr);
-        if (id != BK_NODE_NONE && lane == 0) tr.TN[hd.pend_entry] = hd.pend_tile | (id << 16);
         const int cur = bk_cur(L);
+        bk_tree_link(tr, hd.pend_entry, int(hd.pend_tile), id, cur, lane);
         float val[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) val[i] = value[size_t(g) * 4 + ((i + 4 - cur) & 3)];   // value.rotate_right(cur)
