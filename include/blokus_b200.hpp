@@ -1,0 +1,126 @@
+// blokus_b200.hpp — header-only C++ mirror of the reference's `blokus::game::Game`
+// (blokus/src/game.rs:91-312) over the C ABI of blokus_b200.h.  Value semantics like the Rust type
+// (`Game: Clone`): copying a Game clones the device state (bk_env_clone); Err(String) becomes
+// blokus::Error carrying bk_last_error().  A Game is a batch of one; GameBatch exposes n games.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "blokus_b200.h"
+
+namespace blokus {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+    if (rc < 0) throw Error(rc, bk_last_error());
+}
+
+class GameBatch {
+public:
+    explicit GameBatch(int n_games, int device = 0) : n_(n_games) { check(bk_env_create(n_games, device, &env_)); }
+    GameBatch(const GameBatch& o) : n_(o.n_) { check(bk_env_clone(o.env_, &env_)); }
+    GameBatch(GameBatch&& o) noexcept : n_(o.n_), env_(o.env_) { o.env_ = nullptr; }
+    GameBatch& operator=(GameBatch o) { std::swap(env_, o.env_); std::swap(n_, o.n_); return *this; }
+    ~GameBatch() { bk_env_destroy(env_); }
+
+    int size() const { return n_; }
+    bk_env* handle() const { return env_; }
+    void reset() { check(bk_env_reset(env_)); }                                              // game.rs:102
+    void apply(const std::vector<int32_t>& tiles) { check(bk_env_apply(env_, tiles.data(), nullptr, nullptr)); }
+    void apply(const std::vector<int32_t>& tiles, const std::vector<int32_t>& piece_to_finish) {
+        check(bk_env_apply(env_, tiles.data(), piece_to_finish.data(), nullptr));             // game.rs:150
+    }
+    void place_piece(const std::vector<int32_t>& p, const std::vector<int32_t>& v, const std::vector<int32_t>& o) {
+        check(bk_env_place_piece(env_, p.data(), v.data(), o.data(), nullptr));               // game.rs:116
+    }
+    std::vector<uint8_t> legal_mask() const { return bytes(bk_env_legal_mask, 400); }        // game.rs:242
+    std::vector<uint8_t> board() const { return bytes(bk_env_board, 400); }                  // game.rs:196
+    std::vector<uint8_t> board_state() const { return bytes(bk_env_board_state, 2000); }     // game.rs:283
+    std::vector<uint8_t> anchors(int player = -1) const {                                    // game.rs:238
+        std::vector<uint8_t> out(static_cast<size_t>(n_) * 400);
+        check(bk_env_anchors(env_, player, out.data()));
+        return out;
+    }
+    std::vector<int32_t> current_player() const { return ints(bk_env_current_player, 1); }   // game.rs:225
+    std::vector<int32_t> is_terminal() const { return ints(bk_env_is_terminal, 1); }         // game.rs:275
+    std::vector<int32_t> is_player_active() const { return ints(bk_env_is_player_active, 4); }
+    std::vector<int32_t> scores() const { return ints(bk_env_scores, 4); }                   // game.rs:247
+    std::vector<float> payoff() const {                                                      // game.rs:252
+        std::vector<float> out(static_cast<size_t>(n_) * 4);
+        check(bk_env_payoff(env_, out.data()));
+        return out;
+    }
+    // Game::history of game g as (player, tile) pairs (game.rs:94)
+    std::vector<std::pair<int, int>> history(int g) const {
+        const size_t n = static_cast<size_t>(n_);
+        std::vector<int32_t> cnt(n), pl(n * BK_MAX_PLIES), tl(n * BK_MAX_PLIES);
+        check(bk_env_history(env_, cnt.data(), pl.data(), tl.data()));
+        std::vector<std::pair<int, int>> out;
+        for (int i = 0; i < cnt[size_t(g)]; ++i)
+            out.emplace_back(pl[size_t(g) * BK_MAX_PLIES + size_t(i)], tl[size_t(g) * BK_MAX_PLIES + size_t(i)]);
+        return out;
+    }
+    // lockstep playout on the device (BASELINE.json configs 1-2)
+    void playout(uint64_t seed, uint32_t first_game_id = 0, int max_plies = -1, uint32_t flags = 0) {
+        check(bk_env_playout(env_, seed, first_game_id, max_plies, flags));
+    }
+
+private:
+    template <class F>
+    std::vector<uint8_t> bytes(F fn, size_t per) const {
+        std::vector<uint8_t> out(static_cast<size_t>(n_) * per);
+        check(fn(env_, out.data()));
+        return out;
+    }
+    template <class F>
+    std::vector<int32_t> ints(F fn, size_t per) const {
+        std::vector<int32_t> out(static_cast<size_t>(n_) * per);
+        check(fn(env_, out.data()));
+        return out;
+    }
+    int n_ = 0;
+    bk_env* env_ = nullptr;
+};
+
+// One game with the reference's method names.
+class Game {
+public:
+    static Game reset(int device = 0) { return Game(device); }                               // game.rs:102
+    explicit Game(int device = 0) : b_(1, device) {}
+    void apply(int tile) { b_.apply({tile}); }                                               // apply(tile, None)
+    void apply(int tile, int piece_to_finish) { b_.apply({tile}, {piece_to_finish}); }       // apply(tile, Some(p))
+    Game place_piece(int p, int v, int o) const { Game ns = *this; ns.b_.place_piece({p}, {v}, {o}); return ns; }
+    std::vector<uint8_t> get_board() const { return b_.board(); }
+    int current_player() const { return b_.current_player()[0]; }
+    std::vector<int> get_legal_tiles() const {
+        std::vector<int> out;
+        const auto m = b_.legal_mask();
+        for (int t = 0; t < 400; ++t) if (m[size_t(t)]) out.push_back(t);
+        return out;
+    }
+    std::vector<int> get_current_anchors() const {
+        std::vector<int> out;
+        const auto m = b_.anchors(-1);
+        for (int t = 0; t < 400; ++t) if (m[size_t(t)]) out.push_back(t);
+        return out;
+    }
+    std::vector<int32_t> get_score() const { return b_.scores(); }
+    std::vector<float> get_payoff() const { return b_.payoff(); }
+    bool is_terminal() const { return b_.is_terminal()[0] != 0; }
+    bool is_player_active(int player) const { return b_.is_player_active()[size_t(player)] != 0; }
+    std::vector<uint8_t> get_board_state() const { return b_.board_state(); }
+    std::vector<std::pair<int, int>> history() const { return b_.history(0); }
+    GameBatch& batch() { return b_; }
+
+private:
+    GameBatch b_;
+};
+
+}  // namespace blokus

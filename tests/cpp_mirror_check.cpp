@@ -1,0 +1,31 @@
+// Compiled and run by tests/test_cpp_mirror.py: the C++ mirror of `Game` over the C ABI.
+// Without a CUDA device construction must throw (no CPU fallback); with one, the seed-free "smallest legal
+// tile" game of SURVEY.md Appendix C must come out: 314 plies, scores [15,-35,-4,-3].
+#include <cstdio>
+
+#include "blokus_b200.hpp"
+
+int main() {
+    if (bk_device_count() == 0) {
+        try {
+            blokus::Game g = blokus::Game::reset();
+            std::printf("FAIL: constructed a game without a device\n");
+            return 1;
+        } catch (const blokus::Error& e) {
+            std::printf("no-device ok: [%d] %s\n", e.code, e.what());
+            return e.code == BK_ERR_CUDA ? 0 : 1;
+        }
+    }
+    blokus::Game g = blokus::Game::reset();
+    int plies = 0;
+    while (!g.is_terminal()) { g.apply(g.get_legal_tiles().front()); ++plies; }
+    const auto sc = g.get_score();
+    std::printf("plies %d scores %d %d %d %d\n", plies, sc[0], sc[1], sc[2], sc[3]);
+    bool ok = plies == 314 && sc[0] == 15 && sc[1] == -35 && sc[2] == -4 && sc[3] == -3 && g.history().size() == 314;
+    blokus::Game h = blokus::Game::reset();
+    try { h.apply(399); ok = false; } catch (const blokus::Error& e) { ok = ok && e.code == BK_ERR_ILLEGAL_MOVE; }
+    blokus::Game moved = h.place_piece(0, 0, 0);          // monomino on the start corner; h itself is untouched
+    ok = ok && h.history().empty() && moved.history().size() == 1 && moved.current_player() == 1;
+    std::printf(ok ? "device ok\n" : "FAIL\n");
+    return ok ? 0 : 1;
+}
