@@ -130,7 +130,6 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     uint16_t* __restrict__ h16 = hist + size_t(g) * BK_HIST_CAP;
     uint64_t h = 0ull;
     int steps = 0;
-    BkTurnCache cache = bk_no_cache();
     while (!bk_terminal(G) && (max_plies < 0 || steps < max_plies)) {
         const int cnt = bk_legal_count(G.legal);
         int idx;
@@ -140,7 +139,7 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
         const int tile = bk_legal_select(G.legal, idx, lane);
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;
-        if (!bk_apply(G, tile, -1, lane, tabs, ctr, cache)) break;  // cannot happen: tile came from the legal set
+        if (!bk_apply(G, tile, -1, lane, tabs, ctr)) break;  // cannot happen: tile came from the legal set
         if (lane == 0 && ply < BK_HIST_CAP) h16[ply] = uint16_t(tile | (p << 9));
         if (flags & BK_PLAYOUT_HASH_FLAG) {
             h = bk_splitmix64(h ^ bk_digest(G, lane));

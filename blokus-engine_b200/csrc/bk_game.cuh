@@ -37,14 +37,19 @@ struct __align__(16) BkState {
     uint32_t lastlens;    // byte p = last_piece_lens[p]            (game.rs:98)
     uint32_t t01, t23;    // tiles laid this turn, 16 bits each (at most 4 are ever stored)
     uint32_t ply;         // history length
-    uint32_t pad[3];
+    uint32_t pad[3];      // [0],[1]: child block offset / count when the record is an MCTS node
+    // Narrowing cache of the turn in progress (derived data; meaningful only while |T| >= 1):
+    uint32_t alive;       // chunks of the candidate table with a surviving placement
+    uint32_t tw[3];       // 9x9-window mask of T round T[0]
+    uint16_t smask[32];   // lane l: bit ch set iff candidate ch*32+l is still consistent with T
 };
-static_assert(sizeof(BkState) == 448, "BkState layout");
+static_assert(sizeof(BkState) == 528, "BkState layout");
 
 struct BkRegs {
     uint32_t o0, o1, o2, o3, legal;
     uint32_t pc0, pc1, pc2, pc3;
     uint32_t meta, lastlens, t01, t23, ply;
+    uint32_t smask, alive, tw0, tw1, tw2;   // narrowing cache (see BkState)
 };
 
 struct BkTabs {  // candidate table staged in shared memory
@@ -104,6 +109,9 @@ __device__ __forceinline__ void bk_load(const BkState* __restrict__ s, int lane,
     const uint4 m = *reinterpret_cast<const uint4*>(&s->meta);
     G.meta = m.x; G.lastlens = m.y; G.t01 = m.z; G.t23 = m.w;
     G.ply = s->ply;
+    const uint4 cw = *reinterpret_cast<const uint4*>(&s->alive);
+    G.alive = cw.x; G.tw0 = cw.y; G.tw1 = cw.z; G.tw2 = cw.w;
+    G.smask = s->smask[lane];
 }
 
 __device__ __forceinline__ void bk_store(BkState* __restrict__ s, int lane, const BkRegs& G) {
@@ -115,7 +123,9 @@ __device__ __forceinline__ void bk_store(BkState* __restrict__ s, int lane, cons
         *reinterpret_cast<uint4*>(s->pieces) = make_uint4(G.pc0, G.pc1, G.pc2, G.pc3);
         *reinterpret_cast<uint4*>(&s->meta) = make_uint4(G.meta, G.lastlens, G.t01, G.t23);
         s->ply = G.ply;
+        *reinterpret_cast<uint4*>(&s->alive) = make_uint4(G.alive, G.tw0, G.tw1, G.tw2);
     }
+    s->smask[lane] = uint16_t(G.smask);
 }
 
 __device__ __forceinline__ int bk_cur(const BkRegs& G) { return int(G.meta & 3u); }
@@ -166,20 +176,6 @@ struct BkNarrow {
     bool any_valid;  // some turn-start placement contains T (always true after a legal tile)
 };
 
-// Survivors of the current turn's narrowing, carried in registers by kernels that apply several tiles
-// in a row (the persistent playout).  Stateless callers pass a fresh cache every time.
-struct BkTurnCache {
-    uint32_t smask;      // lane-local: bit ch set iff candidate ch*32+lane is still consistent
-    uint32_t alive;      // warp-uniform: chunks with at least one survivor
-    uint32_t tw0, tw1, tw2;  // window mask of the tiles laid this turn
-    int valid_ply;       // history length the cache belongs to; -1 = nothing cached
-};
-__device__ __forceinline__ BkTurnCache bk_no_cache() {
-    BkTurnCache c;
-    c.smask = 0u; c.alive = 0u; c.tw0 = c.tw1 = c.tw2 = 0u; c.valid_ply = -1;
-    return c;
-}
-
 // window word index / bit of board tile t relative to the window centred on (tr, tc)
 __device__ __forceinline__ void bk_window_bit(int t, int tr, int tc, int& k, uint32_t& b) {
     const int bit = (t / 20 - tr + 4) * 9 + (t % 20 - tc + 4);
@@ -197,11 +193,13 @@ __device__ __forceinline__ uint32_t bk_window_to_row(uint32_t L0, uint32_t L1, u
     return ((slice << tc) >> 4) & BK_ROWMASK;
 }
 
-// S = { turn-start-valid placements containing all nT tiles in T }, evaluated inside the 9x9 window
-// centred on T[0].  free_/anch are the TURN-START rows of this lane.  Fills `cache` with the survivors.
-__device__ __forceinline__ BkNarrow bk_narrow_full(uint32_t free_, uint32_t anch, uint32_t pieces, const int (&T)[5],
-                                                   int nT, int lane, const BkTabs& tabs, BkTurnCache& cache) {
-    const int tr = T[0] / 20, tc = T[0] % 20;
+// First tile t of a turn: S = { turn-start-valid placements containing t }, evaluated inside the 9x9
+// window centred on t (every (variant, cell) candidate contains t by construction).  free_/anch are the
+// TURN-START rows of this lane.  Leaves the survivors in G's narrowing cache.  The 13 chunks are
+// independent, so the loop is fully unrolled: a lone warp (MCTS runs ~2 warps per scheduler) needs the ILP.
+__device__ __forceinline__ BkNarrow bk_narrow_first(BkRegs& G, uint32_t free_, uint32_t anch, uint32_t pieces, int t,
+                                                    int lane, const BkTabs& tabs) {
+    const int tr = t / 20, tc = t % 20;
     const uint32_t fs = ((free_ << 4) >> tc) & 0x1FFu;
     const uint32_t as = ((anch << 4) >> tc) & 0x1FFu;
     const int wr = lane - tr + 4;
@@ -214,119 +212,70 @@ __device__ __forceinline__ BkNarrow bk_narrow_full(uint32_t free_, uint32_t anch
     const uint32_t AW0 = __reduce_or_sync(BK_FULL, wk == 0 ? as << sh : 0u);
     const uint32_t AW1 = __reduce_or_sync(BK_FULL, wk == 1 ? as << sh : 0u);
     const uint32_t AW2 = __reduce_or_sync(BK_FULL, wk == 2 ? as << sh : 0u);
-    uint32_t TW0 = 0u, TW1 = 1u << 13, TW2 = 0u;   // T[0] is the window centre: bit 4*9+4 = 40 = word 1, bit 13
-#pragma unroll
-    for (int i = 1; i < 5; ++i) {
-        if (i < nT) {
-            int k; uint32_t b;
-            bk_window_bit(T[i], tr, tc, k, b);
-            if (k == 0) TW0 |= b; else if (k == 1) TW1 |= b; else TW2 |= b;
-        }
-    }
     uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = 0u;
     int found = 0;
-    if (nT == 1) {
-        // first tile of the turn: every candidate contains T by construction — no "covers" test
-#pragma unroll 1
-        for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
-            if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
-            const int idx = ch * 32 + lane;
-            const uint32_t w0 = tabs.w0[idx];
-            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
-            const uint32_t pid = w0 >> 27;
-            const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
-            const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
-            if (((pieces >> pid) & 1u) && fits && hits) {
-                L0 |= m0; L1 |= m1; L2 |= m2;
-                found = int(pid) + 1;
-                smask |= 1u << ch;
-            }
-        }
-    } else {
-#pragma unroll 1
-        for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
-            if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform
-            const int idx = ch * 32 + lane;
-            const uint32_t w0 = tabs.w0[idx];
-            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
-            const uint32_t pid = w0 >> 27;
-            const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
-            const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
-            const bool covers = (((m0 & TW0) ^ TW0) | ((m1 & TW1) ^ TW1) | ((m2 & TW2) ^ TW2)) == 0u;
-            if (((pieces >> pid) & 1u) && fits && hits && covers) {
-                L0 |= m0; L1 |= m1; L2 |= m2;
-                found = int(pid) + 1;
-                smask |= 1u << ch;
-            }
-        }
-    }
-    L0 = __reduce_or_sync(BK_FULL, L0) & ~TW0;
-    L1 = __reduce_or_sync(BK_FULL, L1) & ~TW1;
-    L2 = __reduce_or_sync(BK_FULL, L2) & ~TW2;
-    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
-    cache.smask = smask;
-    cache.alive = __reduce_or_sync(BK_FULL, smask);
-    cache.tw0 = TW0; cache.tw1 = TW1; cache.tw2 = TW2;
-    BkNarrow out;
-    out.pid = found - 1;
-    out.any_valid = found > 0;
-    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
-    return out;
-}
-
-// Second and later tiles of a turn when the previous tile's survivors are cached: S only shrinks
-// (game.rs:165-173 intersects with the placements through the new tile), so only survivors are
-// re-tested, and only against the new tile.
-__device__ __forceinline__ BkNarrow bk_narrow_incr(const int (&T)[5], int nT, int lane, const BkTabs& tabs,
-                                                   BkTurnCache& cache) {
-    const int tr = T[0] / 20, tc = T[0] % 20;
-    int k; uint32_t b;
-    bk_window_bit(T[nT - 1], tr, tc, k, b);
-    if (k == 0) cache.tw0 |= b; else if (k == 1) cache.tw1 |= b; else cache.tw2 |= b;
-    uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = cache.smask;
-    int found = 0;
-    for (uint32_t cm = cache.alive; cm; cm &= cm - 1u) {   // warp-uniform
-        const int ch = __ffs(cm) - 1;
-        if ((smask >> ch) & 1u) {
-            const int idx = ch * 32 + lane;
-            const uint32_t w0 = tabs.w0[idx];
-            const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
-            const uint32_t mk = k == 0 ? m0 : (k == 1 ? m1 : m2);
-            if (mk & b) {
-                L0 |= m0; L1 |= m1; L2 |= m2;
-                found = int(w0 >> 27) + 1;
-            } else {
-                smask &= ~(1u << ch);
-            }
-        }
-    }
-    L0 = __reduce_or_sync(BK_FULL, L0) & ~cache.tw0;
-    L1 = __reduce_or_sync(BK_FULL, L1) & ~cache.tw1;
-    L2 = __reduce_or_sync(BK_FULL, L2) & ~cache.tw2;
-    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
-    cache.smask = smask;
-    cache.alive = __reduce_or_sync(BK_FULL, smask);
-    BkNarrow out;
-    out.pid = found - 1;
-    out.any_valid = found > 0;
-    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
-    return out;
-}
-
-__device__ __forceinline__ void bk_unpack_T(const BkRegs& G, int (&T)[5], int& nT) {
-    nT = int((G.meta >> 6) & 7u);
-    T[0] = int(G.t01 & 0xFFFFu); T[1] = int(G.t01 >> 16);
-    T[2] = int(G.t23 & 0xFFFFu); T[3] = int(G.t23 >> 16);
-    T[4] = 0;
-}
-
-// this lane's row of the mask of tiles laid this turn
-__device__ __forceinline__ uint32_t bk_T_row(const int (&T)[5], int nT, int lane) {
-    uint32_t m = 0u;
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-        if (i < nT && T[i] / 20 == lane) m |= 1u << (T[i] % 20);
-    return m;
+    for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
+        if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform: no piece of this chunk is held
+        const int idx = ch * 32 + lane;
+        const uint32_t w0 = tabs.w0[idx];
+        const uint32_t m0 = w0 & 0x7FFFFFFu, m1 = tabs.w1[idx], m2 = tabs.w2[idx];
+        const uint32_t pid = w0 >> 27;
+        const bool fits = ((m0 & ~FW0) | (m1 & ~FW1) | (m2 & ~FW2)) == 0u;
+        const bool hits = ((m0 & AW0) | (m1 & AW1) | (m2 & AW2)) != 0u;
+        if (((pieces >> pid) & 1u) && fits && hits) {
+            L0 |= m0; L1 |= m1; L2 |= m2;
+            found = int(pid) + 1;
+            smask |= 1u << ch;
+        }
+    }
+    const uint32_t TW1 = 1u << 13;   // t is the window centre: bit 4*9+4 = 40 = word 1, bit 13
+    L0 = __reduce_or_sync(BK_FULL, L0);
+    L1 = __reduce_or_sync(BK_FULL, L1) & ~TW1;
+    L2 = __reduce_or_sync(BK_FULL, L2);
+    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+    G.smask = smask;
+    G.alive = __reduce_or_sync(BK_FULL, smask);
+    G.tw0 = 0u; G.tw1 = TW1; G.tw2 = 0u;
+    BkNarrow out;
+    out.pid = found - 1;
+    out.any_valid = found > 0;
+    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    return out;
+}
+
+// Later tiles of a turn: S only shrinks (game.rs:165-173 intersects with the placements through the new
+// tile), so only the cached survivors are re-tested, and only against the new tile t.  t0 = T[0].
+__device__ __forceinline__ BkNarrow bk_narrow_next(BkRegs& G, int t0, int t, int lane, const BkTabs& tabs) {
+    const int tr = t0 / 20, tc = t0 % 20;
+    int k; uint32_t b;
+    bk_window_bit(t, tr, tc, k, b);
+    if (k == 0) G.tw0 |= b; else if (k == 1) G.tw1 |= b; else G.tw2 |= b;
+    const uint32_t* __restrict__ wk = k == 0 ? tabs.w0 : (k == 1 ? tabs.w1 : tabs.w2);
+    uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = G.smask;
+    int found = 0;
+    for (uint32_t cm = G.alive; cm; cm &= cm - 1u) {   // warp-uniform
+        const int ch = __ffs(cm) - 1;
+        const int idx = ch * 32 + lane;
+        if (((smask >> ch) & 1u) && (wk[idx] & b)) {
+            const uint32_t w0 = tabs.w0[idx];
+            L0 |= w0 & 0x7FFFFFFu; L1 |= tabs.w1[idx]; L2 |= tabs.w2[idx];
+            found = int(w0 >> 27) + 1;
+        } else {
+            smask &= ~(1u << ch);
+        }
+    }
+    L0 = __reduce_or_sync(BK_FULL, L0) & ~G.tw0;
+    L1 = __reduce_or_sync(BK_FULL, L1) & ~G.tw1;
+    L2 = __reduce_or_sync(BK_FULL, L2) & ~G.tw2;
+    found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+    G.smask = smask;
+    G.alive = __reduce_or_sync(BK_FULL, smask);
+    BkNarrow out;
+    out.pid = found - 1;
+    out.any_valid = found > 0;
+    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    return out;
 }
 
 // position of the k-th (0-based) set bit of a word whose live bits are below bit 32; branch-free
@@ -370,15 +319,7 @@ __device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr)
 // Game::apply(tile, piece_to_finish) (game.rs:150-194).  finish < 0 is None.  Returns false (and
 // leaves the game untouched) when the tile is not legal or finish is out of range.
 __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
-                                         BkCounters& ctr, BkTurnCache& cache);
-// stateless form: narrow from scratch
-__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
                                          BkCounters& ctr) {
-    BkTurnCache cache = bk_no_cache();
-    return bk_apply(G, tile, finish, lane, tabs, ctr, cache);
-}
-__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
-                                         BkCounters& ctr, BkTurnCache& cache) {
     if (tile < 0 || tile >= 400 || bk_terminal(G)) return false;
     const int p = bk_cur(G);
     const int tr = tile / 20, tc = tile % 20;
@@ -390,24 +331,22 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
         fin_pid = bk_nth_set_bit(pieces, finish);
         if (fin_pid < 0) return false;
     }
-    int T[5], nT;
-    bk_unpack_T(G, T, nT);
-    T[nT] = tile;
-    nT += 1;
+    const int nT = int((G.meta >> 6) & 7u) + 1;   // tiles laid this turn, this one included
+    const int t0 = nT > 1 ? int(G.t01 & 0xFFFFu) : tile;
     // Board::place_tile (board.rs:95-141): the square joins own_p; restricted/anchor sets are
     // derived from the bitboards on demand.
     if (p == 0) G.o0 |= bit; else if (p == 1) G.o1 |= bit; else if (p == 2) G.o2 |= bit; else G.o3 |= bit;
     G.ply += 1u;
     BkNarrow nw;
-    if (nT > 1 && cache.valid_ply == int(G.ply) - 1) {
-        nw = bk_narrow_incr(T, nT, lane, tabs, cache);
+    if (nT > 1) {
+        nw = bk_narrow_next(G, t0, tile, lane, tabs);
     } else {
-        const uint32_t trow = bk_T_row(T, nT, lane);
-        const uint32_t mine0 = bk_sel4(p, G.o0, G.o1, G.o2, G.o3) & ~trow;
-        const uint32_t occ0 = (G.o0 | G.o1 | G.o2 | G.o3) & ~trow;
+        // turn-start boards = current boards minus the tile just laid
+        const uint32_t mine0 = bk_sel4(p, G.o0, G.o1, G.o2, G.o3) & ~bit;
+        const uint32_t occ0 = (G.o0 | G.o1 | G.o2 | G.o3) & ~bit;
         uint32_t free_, anch;
         bk_free_anchor(mine0, occ0, p, lane, free_, anch);
-        nw = bk_narrow_full(free_, anch, pieces, T, nT, lane, tabs, cache);
+        nw = bk_narrow_first(G, free_, anch, pieces, tile, lane, tabs);
     }
     const bool done = !__any_sync(BK_FULL, nw.legal != 0u);
     if (done || fin_pid >= 0) {
@@ -419,14 +358,14 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
         G.lastlens = (G.lastlens & ~(0xFFu << (8 * p))) | (len << (8 * p));
         G.meta &= ~(7u << 6);
         G.t01 = 0u; G.t23 = 0u;
-        cache.valid_ply = -1;
         bk_advance(G, lane, ctr);
     } else {
-        cache.valid_ply = int(G.ply);
         G.legal = nw.legal;
         G.meta = (G.meta & ~(7u << 6)) | (uint32_t(nT) << 6);
-        G.t01 = uint32_t(T[0]) | (uint32_t(T[1]) << 16);
-        G.t23 = uint32_t(T[2]) | (uint32_t(T[3]) << 16);
+        if (nT == 1) G.t01 = uint32_t(tile);
+        else if (nT == 2) G.t01 |= uint32_t(tile) << 16;
+        else if (nT == 3) G.t23 = uint32_t(tile);
+        else G.t23 |= uint32_t(tile) << 16;
     }
     return true;
 }
@@ -436,6 +375,7 @@ __device__ __forceinline__ void bk_reset(BkRegs& G, int lane, BkCounters& ctr) {
     G.o0 = G.o1 = G.o2 = G.o3 = 0u;
     G.pc0 = G.pc1 = G.pc2 = G.pc3 = (1u << BK_NUM_PIECES) - 1u;
     G.meta = 0u; G.lastlens = 0u; G.t01 = 0u; G.t23 = 0u; G.ply = 0u;
+    G.smask = 0u; G.alive = 0u; G.tw0 = G.tw1 = G.tw2 = 0u;
     G.legal = bk_movegen_start(G, 0, lane, ctr);
 }
 
