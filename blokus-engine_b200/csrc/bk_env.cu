@@ -148,11 +148,18 @@ static int env_use(const bk_env* e) {
     return BK_OK;
 }
 
-static int env_finish_timed(bk_env* e) {
+// Close a timed kernel region.  sync = false leaves the work enqueued (the stream orders it before any
+// later call of this handle; results are read by calls that synchronise); the elapsed time is then
+// resolved lazily by bk_env_last_kernel_ms.
+static int env_finish_timed(bk_env* e, bool sync) {
     BK_CUDA(cudaEventRecord(e->ev1, e->stream));
     BK_CUDA(cudaGetLastError());
-    BK_CUDA(cudaStreamSynchronize(e->stream));
-    BK_CUDA(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    e->timing_pending = true;
+    if (sync) {
+        BK_CUDA(cudaStreamSynchronize(e->stream));
+        BK_CUDA(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        e->timing_pending = false;
+    }
     return BK_OK;
 }
 
@@ -242,8 +249,7 @@ int bk_env_reset(bk_env* e) {
     BK_LAUNCH(k_reset, grid_for(e->n, BK_STEP_WARPS), 32 * BK_STEP_WARPS, e->stream, e->d_states, e->n);
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(uint16_t) * BK_HIST_CAP * size_t(e->n), e->stream));
-    BK_CUDA(cudaStreamSynchronize(e->stream));
-    return BK_OK;
+    return BK_OK;   // enqueued; every reader synchronises the stream
 }
 
 int bk_env_clone(const bk_env* e, bk_env** out) {
@@ -272,10 +278,11 @@ int bk_env_apply(bk_env* e, const int32_t* tiles, const int32_t* piece_to_finish
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
     BK_LAUNCH(k_apply, grid_for(e->n, BK_STEP_WARPS), 32 * BK_STEP_WARPS, e->stream, 
         e->d_states, e->d_hist, d_tiles, piece_to_finish ? d_fin : nullptr, d_status, e->n, nullptr);
-    rc = env_finish_timed(e);
+    rc = env_finish_timed(e, true);
     if (rc) return rc;
     std::vector<int32_t> st(size_t(e->n));
-    BK_CUDA(cudaMemcpy(st.data(), d_status, nb, cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(st.data(), d_status, nb, cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaStreamSynchronize(e->stream));
     int bad = -1;
     for (int g = 0; g < e->n; ++g) {
         if (status_out) status_out[g] = st[size_t(g)];
@@ -379,7 +386,8 @@ int bk_env_history(bk_env* e, int32_t* counts_out, int32_t* players_out, int32_t
     int rc = env_summary(e, s);
     if (rc) return rc;
     std::vector<uint16_t> h(size_t(e->n) * BK_HIST_CAP);
-    BK_CUDA(cudaMemcpy(h.data(), e->d_hist, sizeof(uint16_t) * h.size(), cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(h.data(), e->d_hist, sizeof(uint16_t) * h.size(), cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaStreamSynchronize(e->stream));
     for (int g = 0; g < e->n; ++g) {
         const int cnt = s[size_t(g)].ply;
         if (counts_out) counts_out[g] = cnt;
@@ -405,7 +413,7 @@ static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const u
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
     BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
               flags, e->d_i32, e->d_hash, e->d_counters);
-    return env_finish_timed(e);
+    return env_finish_timed(e, false);
 }
 
 int bk_env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags) {
@@ -474,6 +482,12 @@ int bk_env_playout_results(bk_env* e, int32_t* steps_out, uint64_t* hash_out) {
 
 int bk_env_last_kernel_ms(bk_env* e, float* ms_out) {
     if (!e || !ms_out) return bk_fail(BK_ERR_INVALID_ARG, "null argument");
+    if (e->timing_pending) {
+        BK_CUDA(cudaSetDevice(e->device));
+        BK_CUDA(cudaEventSynchronize(e->ev1));
+        BK_CUDA(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        e->timing_pending = false;
+    }
     *ms_out = e->last_ms;
     return BK_OK;
 }
@@ -499,7 +513,8 @@ int bk_env_playout_counters(bk_env* e, uint64_t out[3]) {
     int rc = env_use(e);
     if (rc) return rc;
     unsigned long long h[3];
-    BK_CUDA(cudaMemcpy(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < 3; ++i) out[i] = h[i];
     return BK_OK;
 }

@@ -130,12 +130,15 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     uint16_t* __restrict__ h16 = hist + size_t(g) * BK_HIST_CAP;
     uint64_t h = 0ull;
     int steps = 0;
+    BkPlayoutRng rng;
+    rng.w0 = rng.w1 = rng.w2 = rng.w3 = 0u;
+    rng.block = 0xffffffffu;
     while (!bk_terminal(G) && (max_plies < 0 || steps < max_plies)) {
         const int cnt = bk_legal_count(G.legal);
         int idx;
         if (flags & BK_PLAYOUT_MIN_TILE_FLAG) idx = 0;
         else if (flags & BK_PLAYOUT_MAX_TILE_FLAG) idx = cnt - 1;
-        else idx = int(bk_playout_index(seed, game_id, G.ply, uint32_t(cnt)));
+        else idx = int(bk_playout_index(seed, game_id, G.ply, uint32_t(cnt), rng));
         const int tile = bk_legal_select(G.legal, idx, lane);
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;

@@ -40,6 +40,7 @@ struct bk_env {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t uev[2] = {nullptr, nullptr};  // caller-driven region timing
     float last_ms = 0.0f;
+    bool timing_pending = false;
     bool borrowed = false;           // owned by a bk_selfplay
 };
 

@@ -157,7 +157,8 @@ static int sp_use(const bk_selfplay* sp) {
 
 static int sp_check_errors(bk_selfplay* sp) {
     std::vector<BkSearchHdr> h(size_t(sp->n));
-    BK_CUDA(cudaMemcpy(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * h.size(), cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * h.size(), cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     for (int g = 0; g < sp->n; ++g) {
         const uint32_t e = h[size_t(g)].err;
         if (!e) continue;
@@ -209,9 +210,9 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     BK_CUDA(cudaMalloc(&sp->d_pol_visits, sizeof(uint32_t) * size_t(d.policy_cap) * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 8));
     BK_CUDA(cudaMalloc(&sp->d_stage, size_t(n_games) * 400 * 16));
-    BK_CUDA(cudaMemset(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games)));
-    BK_CUDA(cudaMemset(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games)));
-    BK_CUDA(cudaMemset(sp->d_counters, 0, sizeof(unsigned long long) * 8));
+    BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games), sp->env->stream));
+    BK_CUDA(cudaMemsetAsync(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games), sp->env->stream));
+    BK_CUDA(cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned long long) * 8, sp->env->stream));
     // simulation.rs:91-93 — the factor of ucb_score that depends only on the parent's visit count,
     // evaluated on the host with the platform libm exactly as the reference's f32 expression reads
     std::vector<float> ucb(size_t(cfg->sims_per_move) + 2);
@@ -228,6 +229,7 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     BK_CUDA(cudaMalloc(&sp->d_prior, sizeof(float) * prior.size()));
     BK_CUDA(cudaMemcpy(sp->d_ucb, ucb.data(), sizeof(float) * ucb.size(), cudaMemcpyHostToDevice));
     BK_CUDA(cudaMemcpy(sp->d_prior, prior.data(), sizeof(float) * prior.size(), cudaMemcpyHostToDevice));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     d.ucb_tab = sp->d_ucb;
     d.prior_tab = sp->d_prior;
     BK_CUDA(cudaEventCreate(&sp->ev0));
@@ -256,8 +258,8 @@ int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id) {
     if (rc) return rc;
     sp->first_id = first_game_id;
     sp->dcfg.first_game_id = first_game_id;
-    BK_CUDA(cudaMemset(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(sp->n)));
-    BK_CUDA(cudaMemset(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(sp->n)));
+    BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(sp->n), sp->env->stream));
+    BK_CUDA(cudaMemsetAsync(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(sp->n), sp->env->stream));
     return BK_OK;
 }
 
@@ -375,9 +377,11 @@ int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off
     if (rc) return rc;
     const size_t n = size_t(sp->n);
     std::vector<BkSearchHdr> h(n);
-    BK_CUDA(cudaMemcpy(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     std::vector<uint32_t> off(n * (BK_HIST_CAP + 1));
-    BK_CUDA(cudaMemcpy(off.data(), sp->d_pol_off, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(off.data(), sp->d_pol_off, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     for (size_t g = 0; g < n; ++g) {
         const uint32_t plies = h[g].plies_searched;
         if (plies_out) plies_out[g] = int32_t(plies);
@@ -424,7 +428,8 @@ int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]) {
     int rc = sp_use(sp);
     if (rc) return rc;
     unsigned long long h[6];
-    BK_CUDA(cudaMemcpy(h, sp->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    BK_CUDA(cudaMemcpyAsync(h, sp->d_counters, sizeof h, cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     for (int i = 0; i < 6; ++i) out[i] = h[i];
     return BK_OK;
 }

@@ -207,6 +207,14 @@ __device__ __forceinline__ void bk_tree_noise(const BkTree& tr, const BkSearchCf
     __syncwarp();
 }
 
+__device__ __forceinline__ void bk_prefetch_state(const BkState* s, int lane) {
+#ifndef BK_WARP_EMU
+    if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s) + 128 * lane));
+#else
+    (void)s; (void)lane;
+#endif
+}
+
 struct BkLeaf {
     uint32_t parent;  // node whose child entry is the leaf
     uint32_t entry;   // entry index of the leaf
@@ -227,6 +235,9 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
     uint32_t Np = hd.root_visits;
     int depth = 0;
     for (;;) {
+        // If this level's winner turns out to be a leaf, the state of `node` is what the leaf step loads
+        // next: ask L2 for its 5 lines now, one level of latency ahead.
+        bk_prefetch_state(&tr.nodes[node], lane);
         const float F = cfg.ucb_tab[Np];
         float best = 0.0f;
         int bi = -1;
@@ -242,7 +253,13 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
         const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
         if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
-        const uint32_t wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
+        uint32_t wi;
+        if (n <= 32) {
+            // one child per lane: the last maximal child is the highest lane holding the maximum
+            wi = 31u - uint32_t(__clz(int(__ballot_sync(BK_FULL, key == kmax))));
+        } else {
+            wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
+        }
         const int src = int(wi & 31u);                     // child i lives on lane i % 32
         const uint32_t tn = __shfl_sync(BK_FULL, b_tn, src);
         if (depth >= BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; break; }

@@ -33,10 +33,22 @@ __device__ __forceinline__ BkPhilox bk_philox(uint64_t seed, uint32_t c0, uint32
     return o;
 }
 
-// index into n ascending legal tiles for the random-playout policy
-__device__ __forceinline__ uint32_t bk_playout_index(uint64_t seed, uint32_t game, uint32_t ply, uint32_t n) {
-    const BkPhilox b = bk_philox(seed, game, ply, BK_RNG_PLAYOUT, 0u);
-    return __umulhi(b.v[0], n);
+// index into n ascending legal tiles for the random-playout policy: word (ply & 3) of the block keyed by
+// ply >> 2, so a persistent kernel runs Philox once per four plies
+struct BkPlayoutRng {
+    uint32_t w0, w1, w2, w3;
+    uint32_t block;   // ply >> 2 the words belong to; 0xffffffff = none
+};
+__device__ __forceinline__ uint32_t bk_playout_index(uint64_t seed, uint32_t game, uint32_t ply, uint32_t n,
+                                                     BkPlayoutRng& rng) {
+    if (rng.block != (ply >> 2)) {
+        const BkPhilox b = bk_philox(seed, game, ply >> 2, BK_RNG_PLAYOUT, 0u);
+        rng.w0 = b.v[0]; rng.w1 = b.v[1]; rng.w2 = b.v[2]; rng.w3 = b.v[3];
+        rng.block = ply >> 2;
+    }
+    const uint32_t k = ply & 3u;
+    const uint32_t x = k == 0u ? rng.w0 : (k == 1u ? rng.w1 : (k == 2u ? rng.w2 : rng.w3));
+    return __umulhi(x, n);
 }
 
 // u in [0,1) for softmax_sample (simulation.rs:120), exact in f32

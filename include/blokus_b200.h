@@ -131,7 +131,8 @@ int bk_env_digest(bk_env* env, uint64_t* out);
  * more tiles were applied (max_plies < 0: to the end), entirely on the device: legal-tile
  * generation, seeded choice, Game::apply, per ply.  Default policy: ascending legal tiles, index
  * floor(u*n) with u from Philox4x32-10 keyed (seed, first_game_id+g, ply).
- * The env keeps the final states; query them with the bk_env_* calls. */
+ * The env keeps the final states; query them with the bk_env_* calls.  The kernels are ENQUEUED on the
+ * handle's stream and the call returns; any later call that hands data to the host synchronises. */
 int bk_env_playout(bk_env* env, uint64_t seed, uint32_t first_game_id, int max_plies, uint32_t flags);
 /* As bk_env_playout, but game g's global id is game_ids[g] (HOST array of n_games entries, copied to
  * the device inside the call) — the form a sharded driver uses. */

@@ -11,7 +11,8 @@
 // SPEC
 //   block(seed, game, ply, purpose, index) = Philox4x32-10(key = (seed_lo, seed_hi),
 //                                                          ctr = (game, ply, purpose, index))
-//   PLAYOUT (purpose 0): child index = (u64(block(...,0)[0]) * n) >> 32 over ascending legal tiles
+//   PLAYOUT (purpose 0): x = block(seed, game, ply >> 2, PLAYOUT, 0)[ply & 3]  (one block serves four plies);
+//                        child index = (u64(x) * n) >> 32 over ascending legal tiles
 //   ACTION  (purpose 2): u = f32(block(...,0)[0] >> 8) * 2^-24   (simulation.rs:120 stand-in)
 //   NOISE   (purpose 1): Dirichlet([alpha; n]) as normalised Gamma(alpha,1) draws, rand_distr's
 //     published method (alpha<1: Gamma(alpha+1)*U^(1/alpha); Marsaglia-Tsang for shape>=1) done in
@@ -50,8 +51,8 @@ inline Philox4 philox4x32_10(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c
 }
 
 inline uint32_t playout_index(uint64_t seed, uint32_t game, uint32_t ply, uint32_t n) {
-    Philox4 b = philox4x32_10(seed, game, ply, RNG_PLAYOUT, 0);
-    return uint32_t((uint64_t(b.v[0]) * n) >> 32);
+    Philox4 b = philox4x32_10(seed, game, ply >> 2, RNG_PLAYOUT, 0);
+    return uint32_t((uint64_t(b.v[ply & 3]) * n) >> 32);
 }
 
 inline float action_uniform(uint64_t seed, uint32_t game, uint32_t ply) {
