@@ -208,7 +208,7 @@ __device__ __forceinline__ void bk_tree_noise(const BkTree& tr, const BkSearchCf
 }
 
 __device__ __forceinline__ void bk_prefetch_state(const BkState* s, int lane) {
-#ifndef BK_WARP_EMU
+#if !defined(BK_WARP_EMU) && !defined(BK_NO_PREFETCH)
     if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s) + 128 * lane));
 #else
     (void)s; (void)lane;
@@ -239,25 +239,35 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         // next: ask L2 for its 5 lines now, one level of latency ahead.
         bk_prefetch_state(&tr.nodes[node], lane);
         const float F = cfg.ucb_tab[Np];
-        float best = 0.0f;
-        int bi = -1;
-        uint32_t b_tn = 0u, b_n = 0u, b_off = 0u, b_node = 0u;
-        for (int i = lane; i < n; i += 32) {
-            const uint4 sv = tr.S[off + i];
-            const uint4 xv = tr.X[off + i];
-            const float q = __uint_as_float(sv.y);                              // node.rs:33-39 (kept by backup)
-            const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));         // simulation.rs:92-94
-            const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), q); // simulation.rs:95-97
-            if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z; }  // :141
-        }
-        const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
-        const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
-        if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
-        uint32_t wi;
+        uint32_t wi, b_tn = 0u, b_n = 0u, b_off = 0u, b_node = 0u;
         if (n <= 32) {
-            // one child per lane: the last maximal child is the highest lane holding the maximum
+            // one child per lane (the common case): score it, the last maximal child is the highest
+            // lane holding the maximum (`>=` over ascending order, simulation.rs:141)
+            uint32_t key = 0u;
+            if (lane < n) {
+                const uint4 sv = tr.S[off + lane];
+                const uint4 xv = tr.X[off + lane];
+                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));                         // simulation.rs:92-94
+                const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));  // :95-97, Q cached
+                if (sc >= 0.0f) key = __float_as_uint(sc) + 1u;                                     // NaN / negative never wins
+                b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z;
+            }
+            const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
+            if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
             wi = 31u - uint32_t(__clz(int(__ballot_sync(BK_FULL, key == kmax))));
         } else {
+            float best = 0.0f;
+            int bi = -1;
+            for (int i = lane; i < n; i += 32) {
+                const uint4 sv = tr.S[off + i];
+                const uint4 xv = tr.X[off + i];
+                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));
+                const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
+                if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z; }
+            }
+            const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
+            const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
+            if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
             wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
         }
         const int src = int(wi & 31u);                     // child i lives on lane i % 32
