@@ -102,6 +102,8 @@ _SIGNATURES = {
     "bk_selfplay_env": (_P, [_P]),
     "bk_selfplay_results": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "bk_selfplay_last_root": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "bk_selfplay_training_sizes": (C.c_int, [_P, _P, _P]),
+    "bk_selfplay_training_tensors": (C.c_int, [_P, _P, _P, _P]),
     "bk_selfplay_counters": (C.c_int, [_P, _P]),
     "bk_selfplay_last_kernel_ms": (C.c_int, [_P, _P]),
 }

@@ -172,6 +172,31 @@ class SelfPlay:
         return [{"tile": tile[g, : cnt[g]].copy(), "visits": vis[g, : cnt[g]].copy(), "value_sum": w[g, : cnt[g]].copy(),
                  "prior": p[g, : cnt[g]].copy()} for g in range(self.n)]
 
+    def training_tensors(self, xp: str = "torch"):
+        """`save()` of model/training.py:70-119 on the device: (states[P,5,20,20], policies[P,400], values[P,4],
+        ply_offsets[n+1]) over all searched plies P, game-major.  xp="torch": CUDA tensors; xp="numpy": host
+        arrays (CPU-emulator build only)."""
+        total = C.c_int64(0)
+        offs = np.zeros(self.n + 1, dtype=np.int64)
+        self.lib.check(self.lib.bk_selfplay_training_sizes(self._h, C.byref(total), _ptr(offs)))
+        P = max(int(total.value), 1)
+        if xp == "torch":
+            import torch
+            dev = torch.device("cuda", self.env.device)
+            st = torch.empty((P, 5, 20, 20), dtype=torch.float32, device=dev)
+            po = torch.empty((P, 400), dtype=torch.float32, device=dev)
+            va = torch.empty((P, 4), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize(dev)
+            ptrs = [t.data_ptr() for t in (st, po, va)]
+        else:
+            st = np.empty((P, 5, 20, 20), dtype=np.float32)
+            po = np.empty((P, 400), dtype=np.float32)
+            va = np.empty((P, 4), dtype=np.float32)
+            ptrs = [a.ctypes.data for a in (st, po, va)]
+        self.lib.check(self.lib.bk_selfplay_training_tensors(self._h, *[C.c_void_p(p) for p in ptrs]))
+        n = int(total.value)
+        return st[:n], po[:n], va[:n], offs
+
     def game_data(self) -> List[Tuple[list, list, list]]:
         """What training_game() returns for each game (simulation.rs:293-295):
         (history [(player, tile)], policies [[(tile, prob)]], values [4])."""

@@ -28,11 +28,19 @@ struct bk_selfplay {
     float* d_prior = nullptr;
     unsigned long long* d_counters = nullptr;  // [8], cumulative
     uint8_t* d_stage = nullptr;       // [n][400 * 16] gather staging for last_root
+    int64_t* d_ply_off = nullptr;     // [n + 1] prefix of plies per game (training tensors)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.0f;
 };
 
 // ---- kernels ------------------------------------------------------------------------------------------
+__global__ void k_sp_summary(const BkState* __restrict__ states, BkSummary* __restrict__ out, int n) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    kb_summary(states, out, g, lane);
+}
+
 struct BkPools {
     uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr;
     uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
@@ -117,6 +125,21 @@ k_sp_end(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, un
     kb_sp_end(cfg, states, hist, bk_tree_of(pl, cfg, g), &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
               pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, counters, g, lane, tabs,
               wsm);
+}
+
+__global__ void __launch_bounds__(256)
+k_training_tensors(BkSearchCfg cfg, BkPools pl, const uint16_t* hist, const BkSummary* summary, const int64_t* ply_off,
+                   int n, float* states, float* policies, float* values) {
+    __shared__ uint32_t own[80];
+    __shared__ float dense[400];
+    __shared__ uint32_t legal[20];
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const int64_t o = ply_off[g];
+    kb_training_tensors(hist + size_t(g) * BK_HIST_CAP, pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+                        pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap,
+                        int(ply_off[g + 1] - o), summary[g].payoff, states + o * 2000, policies + o * 400, values + o * 4,
+                        own, dense, legal, threadIdx.x, blockDim.x);
 }
 
 // gather the root's child block (tile, visits, value_sum, prior) of every game: out[g][400] x 4 arrays
@@ -245,6 +268,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_scratch); cudaFree(sp->d_hdr); cudaFree(sp->d_pol_off); cudaFree(sp->d_pol_tile);
     cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
     cudaFree(sp->d_stage);
+    cudaFree(sp->d_ply_off);
     if (sp->ev0) cudaEventDestroy(sp->ev0);
     if (sp->ev1) cudaEventDestroy(sp->ev1);
     bk_env_destroy(sp->env);
@@ -421,6 +445,41 @@ int bk_selfplay_last_root(bk_selfplay* sp, int32_t* counts_out, int16_t* tile_ou
     if (value_sum_out) BK_CUDA(cudaMemcpyAsync(value_sum_out, d_w, sizeof(float) * 400 * n, cudaMemcpyDeviceToHost, st));
     if (prior_out) BK_CUDA(cudaMemcpyAsync(prior_out, d_p, sizeof(float) * 400 * n, cudaMemcpyDeviceToHost, st));
     BK_CUDA(cudaStreamSynchronize(st));
+    return BK_OK;
+}
+
+int bk_selfplay_training_sizes(bk_selfplay* sp, int64_t* total_plies_out, int64_t* ply_offset_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    const size_t n = size_t(sp->n);
+    std::vector<BkSearchHdr> h(n);
+    BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    std::vector<int64_t> off(n + 1, 0);
+    for (size_t g = 0; g < n; ++g) off[g + 1] = off[g] + int64_t(h[g].plies_searched);
+    if (!sp->d_ply_off) BK_CUDA(cudaMalloc(&sp->d_ply_off, sizeof(int64_t) * (n + 1)));
+    BK_CUDA(cudaMemcpyAsync(sp->d_ply_off, off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    if (total_plies_out) *total_plies_out = off[n];
+    if (ply_offset_out) for (size_t g = 0; g <= n; ++g) ply_offset_out[g] = off[g];
+    return BK_OK;
+}
+
+int bk_selfplay_training_tensors(bk_selfplay* sp, float* dev_states, float* dev_policies, float* dev_values) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!dev_states || !dev_policies || !dev_values) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_training_tensors: null output");
+    if (!sp->d_ply_off) return bk_fail(BK_ERR_STATE, "bk_selfplay_training_tensors: call bk_selfplay_training_sizes first");
+    cudaStream_t st = sp->env->stream;
+    // payoffs come from the games' final states
+    BK_LAUNCH(k_sp_summary, (sp->n + 3) / 4, 128, st, sp->env->d_states, sp->env->d_summary, sp->n);
+    BK_CUDA(cudaEventRecord(sp->ev0, st));
+    BK_LAUNCH(k_training_tensors, sp->n, 256, st, sp->dcfg, pools_of(sp), sp->env->d_hist, sp->env->d_summary, sp->d_ply_off,
+              sp->n, dev_states, dev_policies, dev_values);
+    BK_CUDA(cudaEventRecord(sp->ev1, st));
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(cudaEventElapsedTime(&sp->last_ms, sp->ev0, sp->ev1));
     return BK_OK;
 }
 

@@ -575,3 +575,54 @@ __device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __res
         atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
     }
 }
+
+
+// ---- training tensors (the consumer side, model/training.py:70-119 `save()`), built on the device -------------
+// For ply i of a game with mover p: planes 0..3 = squares laid BEFORE ply i by seats p, p+1, p+2, p+3; plane 4 =
+// the tiles of the recorded policy (the root's children); all turned p quarter turns (torch.rot90(k=p)); the dense
+// policy (visits / total visits, f32) turned the same way; the game's payoff repeated.  One CTA per game walks its
+// plies in order with the running bitboards in shared memory; every thread writes a coalesced slice per ply.
+__device__ __forceinline__ void kb_training_tensors(const uint16_t* __restrict__ hist, const uint32_t* __restrict__ pol_off,
+                                                    const uint16_t* __restrict__ pol_tile,
+                                                    const uint32_t* __restrict__ pol_visits, int plies,
+                                                    const float* __restrict__ payoff4, float* __restrict__ states,
+                                                    float* __restrict__ policies, float* __restrict__ values,
+                                                    uint32_t* own /* shared [4][20] */, float* dense /* shared [400] */,
+                                                    uint32_t* legal /* shared [20] */, int tid, int nthreads) {
+    for (int i = tid; i < 80; i += nthreads) own[i] = 0u;
+    __syncthreads();
+    for (int ply = 0; ply < plies; ++ply) {
+        const uint32_t h = hist[ply];
+        const int p = int(h >> 9), tile = int(h & 0x1FFu);
+        const uint32_t a = pol_off[ply], b = pol_off[ply + 1];
+        for (int i = tid; i < 400; i += nthreads) dense[i] = 0.0f;
+        for (int i = tid; i < 20; i += nthreads) legal[i] = 0u;
+        __syncthreads();
+        uint32_t total = 0u;
+        for (uint32_t e = a; e < b; ++e) total += pol_visits[e];           // every thread: <= 400 cached loads
+        const float ft = float(total);
+        for (uint32_t e = a + uint32_t(tid); e < b; e += uint32_t(nthreads)) {
+            const int t = int(pol_tile[e]);
+            dense[t] = __fdiv_rn(float(pol_visits[e]), ft);                // simulation.rs:222
+            atomicOr(&legal[t / 20], 1u << (t % 20));
+        }
+        __syncthreads();
+        float* st = states + size_t(ply) * 2000;
+        float* po = policies + size_t(ply) * 400;
+        for (int e = tid; e < 2000; e += nthreads) {
+            const int plane = e / 400, j = (e % 400) / 20, k = e % 20;
+            int r, c;
+            if (p == 0) { r = j; c = k; }
+            else if (p == 1) { r = k; c = 19 - j; }
+            else if (p == 2) { r = 19 - j; c = 19 - k; }
+            else { r = 19 - k; c = j; }
+            const uint32_t row = plane < 4 ? own[((plane + p) & 3) * 20 + r] : legal[r];
+            st[e] = float((row >> c) & 1u);
+            if (plane == 0) po[e] = dense[r * 20 + c];
+        }
+        for (int e = tid; e < 4; e += nthreads) values[size_t(ply) * 4 + e] = payoff4[e];
+        __syncthreads();
+        if (tid == 0) own[p * 20 + tile / 20] |= 1u << (tile % 20);       // "make the move that was made"
+        __syncthreads();
+    }
+}

@@ -224,6 +224,17 @@ int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off
  * [g][400] tile, visits, value_sum, prior. */
 int bk_selfplay_last_root(bk_selfplay* sp, int32_t* counts_out, int16_t* tile_out, uint32_t* visits_out,
                           float* value_sum_out, float* prior_out);
+/* The consumer side — model/training.py:70-119 `save()` — on the device: for every
+ * searched ply of every game, in game-major order, the training triple
+ *   states[ply][5][20][20]  planes 0..3 = squares laid before the ply by seats mover, mover+1, ..; plane 4 = the
+ *                           recorded policy's tiles; rotated `mover` quarter turns (torch.rot90(k=mover))
+ *   policies[ply][400]      visits / total visits (f32), rotated the same way
+ *   values[ply][4]          the game's payoff (absolute seat order), repeated
+ * bk_selfplay_training_sizes returns the total number of plies and the per-game prefix offsets (n_games + 1
+ * entries; either pointer may be NULL) and must be called first; bk_selfplay_training_tensors fills DEVICE
+ * buffers of total*2000, total*400 and total*4 floats. */
+int bk_selfplay_training_sizes(bk_selfplay* sp, int64_t* total_plies_out, int64_t* ply_offset_out);
+int bk_selfplay_training_tensors(bk_selfplay* sp, float* dev_states, float* dev_policies, float* dev_values);
 /* Counters since creation: [0] simulations, [1] Game::apply calls, [2] turn-start move generations,
  * [3] sum of 120*C_rem, [4] child entries created, [5] nodes expanded. */
 int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]);

@@ -334,3 +334,30 @@ def check_play_training_game(lib, orc, cfg_kwargs, game_id=7):
     # one request per evaluated position: the root of every ply plus every non-terminal leaf
     assert q.requests >= ref["n_plies"]
     return len(history)
+
+
+def check_training_tensors(lib, orc, n_games, cfg_kwargs, max_plies, xp):
+    """Device-side `save()` (model/training.py:70-119) against its numpy restatement applied to the tuples
+    the same run returns — and the state planes against Game::get_board_state of the oracle game at that ply."""
+    from blokus_self_play import SelfPlay, Config
+    from oracle.save_oracle import save_arrays
+    sp = SelfPlay(n_games, Config(**cfg_kwargs), first_game_id=2, lib=lib)
+    sp.run_stub(max_plies)
+    st, po, va, offs = sp.training_tensors(xp=xp)
+    if xp == "torch":
+        st, po, va = st.cpu().numpy(), po.cpu().numpy(), va.cpu().numpy()
+    data = sp.game_data()
+    assert offs[-1] == sum(len(d[0]) for d in data) == len(st)
+    for g, game in enumerate(data):
+        rs, rp, rv = save_arrays(game)
+        a, b = int(offs[g]), int(offs[g + 1])
+        assert np.array_equal(st[a:b], rs), f"states differ, game {g}"
+        assert np.array_equal(po[a:b], rp), f"policies differ, game {g}"
+        assert np.array_equal(va[a:b], rv), f"values differ, game {g}"
+        # with the stub every legal tile is a root child, so the planes equal get_board_state() ply by ply
+        og = orc.Game()
+        for i, (_, tile) in enumerate(game[0]):
+            assert np.array_equal(st[a + i], og.board_state().astype(np.float32)), f"planes != get_board_state, game {g} ply {i}"
+            og.apply(tile)
+    sp.close()
+    return len(st)

@@ -38,3 +38,10 @@ def test_emu_external_stub_equals_fused_kernel(emu_lib, orc):
             assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
     for x, y in zip(a.last_root(), b.last_root()):
         assert np.array_equal(x["prior"], y["prior"]) and np.array_equal(x["value_sum"], y["value_sum"])
+
+
+def test_emu_training_tensors(emu_lib, orc):
+    n = parity.check_training_tensors(emu_lib, orc, 1, dict(sims_per_move=6, sample_moves=2, c_base=19652, c_init=1.25,
+                                                            dirichlet_alpha=0.3, exploration_fraction=0.25, seed=1),
+                                      max_plies=9, xp="numpy")
+    assert n == 9

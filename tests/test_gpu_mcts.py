@@ -95,3 +95,9 @@ def test_gpu_external_stub_equals_fused_kernel(cuda_lib, orc):
     for ra, rb in zip(a.policy_records(), b.policy_records()):
         for (t1, v1), (t2, v2) in zip(ra, rb):
             assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+
+
+def test_gpu_training_tensors(cuda_lib, orc):
+    """model/training.py `save()` on the device, whole games, bit-exact."""
+    n = parity.check_training_tensors(cuda_lib, orc, 6, dict(CONFIG3, sims_per_move=24, seed=8), max_plies=-1, xp="torch")
+    assert n > 6 * 230
