@@ -284,14 +284,21 @@ def main() -> int:
     clocks = sampler.stop()
 
     # ---- end-to-end timed region (host buffers in and out, every step) -----------------------------
+    for w in range(args.warmup):          # the GPU idled while the clock sampler was read: warm up again
+        e2e_step(2000 + w)
     barrier()
     t0 = time.perf_counter()
     e2e_moves = 0
+    per_step = []
     for k in range(args.steps):
+        ts = time.perf_counter()
         e2e_step(k)
         e2e_moves += int(plies_h.sum().item())
+        per_step.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("BK_DEBUG"):
+        print("e2e per-step us:", [round(1e6 * x) for x in per_step], file=sys.stderr)
     barrier()
 
     # ---- secondary metric: MCTS sims/s (configs[2]) -------------------------------------------------
