@@ -7,3 +7,4 @@ from ._lib import (BkConfig, BkError, Lib, default_lib, DEFAULT_LIB, MAX_PLIES, 
                    ERR_ILLEGAL_MOVE, ERR_CUDA, ERR_INVALID_ARG, ERR_CAPACITY, ERR_STATE)
 from .game import Game, GameBatch, probe_int_peak  # noqa: F401
 from .selfplay import Config, SelfPlay, play_training_games, play_training_game, host_evaluator  # noqa: F401
+from .arena import play_test_game, play_test_games  # noqa: F401

@@ -228,4 +228,38 @@ inline GameRecord training_game(const Config& cfg, const Evaluator& ev, int id, 
     return rec;
 }
 
+// simulation.rs:233-265.  The random baseline move draws gen_range(0..n) from thread_rng (:250) and takes
+// keys().nth(index) of a HashMap; canonical form: ascending children, index from the seeded SPEC
+// (purpose 3, same multiply-shift as the playout policy).
+inline size_t best_action(const Game& game, const Evaluator& ev, int id, uint64_t seed) {
+    Node root(0.0f);
+    evaluate(root, game, ev, id);
+    if (game.current_player() != 0) {
+        const size_t n = root.children.size();
+        Philox4 b = philox4x32_10(seed, uint32_t(id), uint32_t(game.history.size()), 3u, 0u);
+        size_t index = size_t((uint64_t(b.v[0]) * n) >> 32);
+        auto it = root.children.begin();
+        std::advance(it, long(index));
+        return it->first;
+    }
+    float highest_prior = 0.0f;
+    size_t best = 0;
+    for (const auto& kv : root.children)
+        if (kv.second.prior > highest_prior) { highest_prior = kv.second.prior; best = kv.first; }
+    return best;
+}
+
+// simulation.rs:298-332: seat 0 asks `model`, the other seats ask `baseline`; returns payoff[0]
+inline float test_game(int id, const Evaluator& model, const Evaluator& baseline, uint64_t seed,
+                       std::vector<std::pair<int, int>>* history_out = nullptr) {
+    Game game = Game::reset();
+    while (!game.is_terminal()) {
+        const Evaluator& q = game.current_player() == 0 ? model : baseline;
+        size_t action = best_action(game, q, id, seed);
+        (void)game.apply(action, -1);
+    }
+    if (history_out) *history_out = game.history;
+    return game.get_payoff()[0];
+}
+
 }  // namespace orc

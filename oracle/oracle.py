@@ -75,6 +75,8 @@ def lib():
         L.orc_selfplay_game.argtypes = [C.POINTER(OrcConfig), C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6
         L.orc_selfplay_batch.argtypes = [C.POINTER(OrcConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_selfplay_batch.restype = C.c_double
+        L.orc_test_game.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_test_game.restype = C.c_float
         L.orc_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.orc_playout_index.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_playout_index.restype = C.c_uint32
@@ -295,6 +297,26 @@ def selfplay_game(cfg, game_id, max_plies=-1, evaluator=None, root_cap=1 << 17):
         roots.append({"tile": r_tile[a:b].copy(), "visits": r_vis[a:b].copy(), "value_sum": r_w[a:b].copy(), "prior": r_p[a:b].copy()})
     # history may be one longer than n when max_plies cut the game; only n plies were searched
     return {"n_plies": n, "players": players[:n].copy(), "tiles": tiles[:n].copy(), "roots": roots, "payoff": payoff, "sims": sims.value}
+
+
+def _wrap_eval(evaluator):
+    def _cb(_user, gid, planes, policy, value):
+        pl = np.ctypeslib.as_array(planes, shape=(2000,)).reshape(5, 20, 20)
+        pol, val = evaluator(gid, pl)
+        np.ctypeslib.as_array(policy, shape=(400,))[:] = np.asarray(pol, dtype=np.float32)
+        np.ctypeslib.as_array(value, shape=(4,))[:] = np.asarray(val, dtype=np.float32)
+    return EVAL_FN(_cb)
+
+
+def test_game(game_id, model, baseline, seed=0):
+    """play_test_game (simulation.rs:298-332): model / baseline are evaluator(id, planes) -> (policy, value)."""
+    players = np.zeros(400, dtype=np.int32)
+    tiles = np.zeros(400, dtype=np.int32)
+    n = C.c_int(0)
+    m, b = _wrap_eval(model), _wrap_eval(baseline)
+    score = lib().orc_test_game(game_id, seed, C.cast(m, C.c_void_p), C.cast(b, C.c_void_p), None, players.ctypes.data,
+                                tiles.ctypes.data, C.addressof(n))
+    return {"score": float(score), "players": players[: n.value].copy(), "tiles": tiles[: n.value].copy()}
 
 
 def selfplay_batch(cfg, first_game, n_games, n_threads=1, max_plies=-1):

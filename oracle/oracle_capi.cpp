@@ -285,6 +285,25 @@ int orc_selfplay_game(const OrcConfig* c, int game_id, int max_plies, orc_eval_f
     return n;
 }
 
+// play_test_game (simulation.rs:298-332) with two caller-supplied evaluators; returns payoff[0]
+float orc_test_game(int game_id, uint64_t seed, orc_eval_fn model, orc_eval_fn baseline, void* user, int* players,
+                    int* tiles, int* n_plies) {
+    auto wrap = [user](orc_eval_fn fn) {
+        return Evaluator([fn, user](int id, const Planes& p, std::vector<float>& pol, std::vector<float>& val) {
+            uint8_t flat[2000];
+            for (size_t a = 0; a < 5; ++a) for (size_t r = 0; r < 20; ++r) for (size_t cc = 0; cc < 20; ++cc) flat[(a * 20 + r) * 20 + cc] = p[a][r][cc];
+            pol.assign(400, 0.0f);
+            val.assign(4, 0.0f);
+            fn(user, id, flat, pol.data(), val.data());
+        });
+    };
+    std::vector<std::pair<int, int>> hist;
+    float r = test_game(game_id, wrap(model), wrap(baseline), seed, &hist);
+    for (size_t i = 0; i < hist.size(); ++i) { if (players) players[i] = hist[i].first; if (tiles) tiles[i] = hist[i].second; }
+    if (n_plies) *n_plies = int(hist.size());
+    return r;
+}
+
 // n_games stub-evaluator games over n_threads threads, each cut at max_plies; returns wall seconds.
 double orc_selfplay_batch(const OrcConfig* c, int first_game, int n_games, int n_threads, int max_plies,
                           int64_t* sims) {

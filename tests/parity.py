@@ -361,3 +361,30 @@ def check_training_tensors(lib, orc, n_games, cfg_kwargs, max_plies, xp):
             og.apply(tile)
     sp.close()
     return len(st)
+
+
+def check_arena(lib, orc, n_games=2, seed=5):
+    """play_test_game / play_test_games (simulation.rs:233-265,298-332) against the oracle's restatement."""
+    from blokus_self_play import play_test_games, play_test_game
+    bm, sm = fixed_network(11)
+    bb, sb = fixed_network(12)
+    ids = list(range(30, 30 + n_games))
+    scores, hists = play_test_games(ids, bm, bb, seed=seed, lib=lib)
+    for g, gid in enumerate(ids):
+        ref = orc.test_game(gid, sm, sb, seed=seed)
+        assert [t for _, t in hists[g]] == ref["tiles"].tolist(), f"arena trace differs, game {gid}"
+        assert [p for p, _ in hists[g]] == ref["players"].tolist()
+        assert scores[g] == ref["score"]
+    # the reference's own signature and IPC protocol, one game
+    qm, qb = FakeQueue(sm), FakeQueue(sb)
+    shared = []
+    qm.answers = shared
+    qb.answers = shared
+
+    class Pipe:
+        def recv(self):
+            return shared.pop(0)
+    s = play_test_game(ids[0], qm, qb, Pipe(), seed=seed, lib=lib)
+    assert s == scores[0]
+    assert qm.requests > 0 and qb.requests > 0 and qm.requests + qb.requests == len(hists[0])
+    return scores

@@ -45,3 +45,7 @@ def test_emu_training_tensors(emu_lib, orc):
                                                             dirichlet_alpha=0.3, exploration_fraction=0.25, seed=1),
                                       max_plies=9, xp="numpy")
     assert n == 9
+
+
+def test_emu_arena_play_test_game(emu_lib, orc):
+    parity.check_arena(emu_lib, orc, n_games=1, seed=2)

@@ -101,3 +101,8 @@ def test_gpu_training_tensors(cuda_lib, orc):
     """model/training.py `save()` on the device, whole games, bit-exact."""
     n = parity.check_training_tensors(cuda_lib, orc, 6, dict(CONFIG3, sims_per_move=24, seed=8), max_plies=-1, xp="torch")
     assert n > 6 * 230
+
+
+def test_gpu_arena_play_test_game(cuda_lib, orc):
+    """play_test_game / arena on the B200 game engine."""
+    parity.check_arena(cuda_lib, orc, n_games=6, seed=5)
