@@ -1,0 +1,82 @@
+"""Hand-written tensor-core leaf evaluator: the ResNet trunk's 3x3 convolutions run on
+`bk_conv3x3_bf16` (tcgen05 / TMEM / TMA, csrc/bk_conv.cu); the 5-channel input convolution and the two tiny heads
+stay in PyTorch.  BatchNorm (eval mode) is folded into the convolution weights and bias:
+    y = gamma * (conv(x) + b - mean) / sqrt(var + eps) + beta  =  conv_{w * s}(x) + ((b - mean) * s + beta),  s = gamma / sqrt(var + eps)
+Activations stay in the kernel's zero-padded NHWC bf16 layout [batch*441][256] for the whole trunk."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .resnet import ResNet
+
+PAD = 21
+
+
+def to_padded_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[B, C, 20, 20] -> bf16 [B*441, C] (row 20 / col 20 of every image are zeros)."""
+    b, c = x.shape[0], x.shape[1]
+    return F.pad(x, (0, 1, 0, 1)).permute(0, 2, 3, 1).reshape(b * PAD * PAD, c).to(torch.bfloat16).contiguous()
+
+
+def from_padded_nhwc(y: torch.Tensor, batch: int) -> torch.Tensor:
+    """bf16 [B*441, C] -> float32 [B, C, 20, 20]."""
+    return y.reshape(batch, PAD, PAD, -1)[:, :20, :20, :].permute(0, 3, 1, 2).float().contiguous()
+
+
+def fold_conv_bn(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
+    """-> (w bf16 [9][out][in], bias f32 [out]) with the eval-mode BatchNorm folded in."""
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight * s[:, None, None, None]
+    b = (conv.bias - bn.running_mean) * s + bn.bias
+    w9 = w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1])           # tap = ky*3 + kx
+    return w9.to(torch.bfloat16).contiguous(), b.float().contiguous()
+
+
+def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor], relu: bool,
+            batch: int, out: Optional[torch.Tensor] = None, lib=None) -> torch.Tensor:
+    lib = lib or _lib.default_lib()
+    y = out if out is not None else torch.empty_like(x)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    lib.check(lib.bk_conv3x3_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(w9.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                  C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                                  C.c_void_p(y.data_ptr()), batch, 1 if relu else 0, C.c_void_p(stream)))
+    return y
+
+
+class TensorCoreLeafEvaluator:
+    """Callable evaluator for SelfPlay.run_evaluator; same contract as resnet.LeafEvaluator (eval mode)."""
+
+    def __init__(self, model: ResNet, lib=None):
+        if model.width != 256:
+            raise ValueError("the tcgen05 trunk kernel is built for width 256 (BASELINE.json config 4)")
+        self.model = model.eval()
+        self.lib = lib or _lib.default_lib()
+        with torch.no_grad():
+            self.blocks = [(fold_conv_bn(b.conv1, b.bn1), fold_conv_bn(b.conv2, b.bn2)) for b in model.res_blocks]
+        self._bufs = {}
+
+    @torch.no_grad()
+    def __call__(self, planes: torch.Tensor):
+        m = self.model
+        batch = planes.shape[0]
+        key = (batch, planes.device)
+        if key not in self._bufs:
+            self._bufs[key] = [torch.zeros((batch * PAD * PAD, 256), dtype=torch.bfloat16, device=planes.device) for _ in range(3)]
+        a, t, b = self._bufs[key]
+        x = to_padded_nhwc(m.input(planes))                       # 5 -> 256 input convolution (library; 0.5 % of the FLOPs)
+        a.copy_(x)
+        for (w1, b1), (w2, b2) in self.blocks:
+            conv3x3(a, w1, b1, None, True, batch, out=t, lib=self.lib)        # relu(bn1(conv1(x)))
+            conv3x3(t, w2, b2, a, True, batch, out=b, lib=self.lib)           # relu(bn2(conv2(.)) + x)
+            a, b = b, a
+        feat = from_padded_nhwc(a, batch)
+        legal = planes[:, 4].reshape(batch, -1)
+        logits = m.policy_head(feat)
+        policy = torch.softmax(logits * legal + (1 - legal) * -1e9, dim=1) * legal
+        value = torch.softmax(m.value_head(feat), dim=1)
+        return policy, value

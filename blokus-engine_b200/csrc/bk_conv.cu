@@ -1,0 +1,269 @@
+// bk_conv.cu — hand-written sm_100a tensor-core kernel for the one dense contraction on the path: the
+// 3x3 convolutions of the reference's policy/value ResNet trunk (model/resnet.py:8-26,51-52;
+// SURVEY.md §8f row f2).  tcgen05.mma with the accumulator in TMEM, operands staged by TMA into
+// 128B-swizzled shared memory, BatchNorm folded into weights/bias, bias + residual + ReLU fused into the
+// epilogue that reads TMEM with tcgen05.ld.
+//
+// Formulation.  Activations live in HBM as a zero-padded NHWC matrix X[m][c], bf16, with
+// m = image*441 + row*21 + col (row, col in 0..20; row 20 and col 20 are zero padding shared by neighbours),
+// so a 3x3 tap (dy, dx) is a pure row shift of dy*21 + dx and the convolution is nine shifted GEMMs
+//     Y[m][n] = sum_tap sum_k X[m + dy*21 + dx][k] * W[tap][n][k]
+// whose A tiles are plain 2-D TMA boxes (out-of-range rows are zero-filled by TMA).  One CTA computes a
+// 128-row x 256-channel output tile: 9 taps x 4 K-chunks of 64 = 36 pipeline steps of {A 16 KB, B 32 KB},
+// each 4 UMMA instructions M128 N256 K16 into 256 TMEM columns.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp-in-warpgroup rank).
+#include "bk_host.h"
+
+#ifndef BK_WARP_EMU
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <map>
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;
+constexpr int kChannels = 256;
+constexpr int kStages = 4;
+constexpr int kTaps = 9;
+constexpr int kStepsPerTap = kChannels / kBlockK;          // 4
+constexpr int kSteps = kTaps * kStepsPerTap;               // 36
+constexpr uint32_t kBytesA = kBlockM * kBlockK * 2;        // 16 KB
+constexpr uint32_t kBytesB = kBlockN * kBlockK * 2;        // 32 KB
+constexpr uint32_t kBytesStage = kBytesA + kBytesB;
+constexpr uint32_t kSmemBytes = kStages * kBytesStage + 256 + 1024;   // + barriers + alignment slack
+constexpr uint32_t kTmemCols = 256;
+constexpr int kPadDim = 21;
+constexpr int kPadImage = kPadDim * kPadDim;               // 441
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFFu);          // start address
+    d |= uint64_t(1) << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t((1024u >> 4) & 0x3FFFu) << 32;         // stride byte offset
+    d |= uint64_t(1) << 46;                              // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                              // SWIZZLE_128B
+    return d;
+}
+// D(f32) += A(bf16, K-major) * B(bf16, K-major)^T, M = 128, N = 256
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kBlockN >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// Y = act(conv3x3(X) + bias [+ R]) on the padded NHWC layout; pad rows of Y are written as zeros.
+__global__ void __launch_bounds__(192, 1)
+k_conv3x3_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+             const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+             int m_total, int relu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages * kBytesStage;
+    auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(kStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * uint32_t(2 * kStages);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStages * kBytesStage + 8 * (2 * kStages + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int ks = 0; ks < kSteps; ++ks) {
+                const int s = ks % kStages;
+                const uint32_t ph = uint32_t(ks / kStages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), kBytesStage);
+                const int tap = ks / kStepsPerTap, kc = ks % kStepsPerTap;
+                const int shift = (tap / 3 - 1) * kPadDim + (tap % 3 - 1);
+                const uint32_t a_dst = smem_base + uint32_t(s) * kBytesStage;
+                tma_load_2d(a_dst, &map_x, full_bar(s), kc * kBlockK, m0 + shift);
+                tma_load_2d(a_dst + kBytesA, &map_w, full_bar(s), kc * kBlockK, tap * kBlockN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int ks = 0; ks < kSteps; ++ks) {
+                const int s = ks % kStages;
+                const uint32_t ph = uint32_t(ks / kStages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_base + uint32_t(s) * kBytesStage;
+                const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + kBytesA);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)       // 32 bytes (16 bf16) further along K = +2 in 16-byte units
+                    umma_f16(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), (ks > 0 || k > 0) ? 1u : 0u);
+                umma_commit(empty_bar(s));                    // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);                       // accumulator complete
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int wq = warp & 3;                              // TMEM lane quarter this warp may read
+        const int m = m0 + wq * 32 + lane;
+        const int pos = m % kPadImage;
+        const bool live = m < m_total;
+        const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
+        uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
+        const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < kBlockN / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(cc * 32), v);
+            if (!live) continue;
+            uint32_t packed[16];
+            if (pad) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) packed[j] = 0u;
+            } else {
+                uint4 r4[4];
+                if (rrow) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                }
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
+                    float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
+                    if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
+                    if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                    packed[j] = pack_bf16(a, b);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][256] bf16 matrix, box = 64 channels x box_rows rows, 128B swizzle, zero fill outside
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return bk_fail(BK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {kChannels, rows};
+    const cuuint64_t strides[1] = {kChannels * 2};
+    const cuuint32_t box[2] = {kBlockK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bk_fail(BK_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+    return BK_OK;
+}
+
+}  // namespace
+#endif  // BK_WARP_EMU
+
+extern "C" int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual,
+                               void* dev_y, int batch, int relu, void* cuda_stream) {
+#ifdef BK_WARP_EMU
+    (void)dev_x; (void)dev_w; (void)dev_bias; (void)dev_residual; (void)dev_y; (void)batch; (void)relu; (void)cuda_stream;
+    return bk_fail(BK_ERR_STATE, "bk_conv3x3_bf16: tensor-core kernel, not available in the CPU emulator build");
+#else
+    if (!dev_x || !dev_w || !dev_bias || !dev_y || batch <= 0) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: bad argument");
+    static bool attr_set = false;
+    if (!attr_set) {
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        attr_set = true;
+    }
+    const int m_total = batch * kPadImage;
+    CUtensorMap map_x, map_w;
+    int rc = make_map(&map_x, dev_x, uint64_t(m_total), kBlockM);
+    if (rc) return rc;
+    rc = make_map(&map_w, dev_w, uint64_t(kTaps) * kBlockN, kBlockN);
+    if (rc) return rc;
+    const int tiles = (m_total + kBlockM - 1) / kBlockM;
+    k_conv3x3_tc<<<tiles, 192, kSmemBytes, static_cast<cudaStream_t>(cuda_stream)>>>(
+        map_x, map_w, dev_bias, static_cast<const __nv_bfloat16*>(dev_residual), static_cast<__nv_bfloat16*>(dev_y), m_total, relu);
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+#endif
+}

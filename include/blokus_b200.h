@@ -240,6 +240,17 @@ int bk_selfplay_training_tensors(bk_selfplay* sp, float* dev_states, float* dev_
 int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]);
 int bk_selfplay_last_kernel_ms(bk_selfplay* sp, float* ms_out);
 
+/* ---- leaf evaluator building block ------------------------------------------------ */
+/* One 3x3 convolution of the reference's ResNet trunk (model/resnet.py:13-14: Conv2d(C, C, 3, padding=1) with
+ * C = 256) as a hand-written tcgen05/TMEM/TMA kernel, BatchNorm folded by the caller into w/bias:
+ *     y = act(conv3x3(x) + bias [+ residual])
+ * All pointers are DEVICE memory.  x, residual, y: bf16, zero-padded NHWC [batch*441][256] with row index
+ * image*441 + r*21 + c (r, c in 0..20; r == 20 and c == 20 are zero padding and stay zero in y).
+ * w: bf16 [9 taps][256 out][256 in], tap = (dy+1)*3 + (dx+1).  bias: f32 [256].  residual may be NULL.
+ * relu != 0 applies ReLU.  The kernel is enqueued on cuda_stream (a cudaStream_t passed as void*). */
+int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual,
+                    void* dev_y, int batch, int relu, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
