@@ -90,6 +90,7 @@ _SIGNATURES = {
     "bk_env_event_elapsed": (C.c_int, [_P, _P]),
     "bk_env_playout_counters": (C.c_int, [_P, _P]),
     "bk_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "bk_conv3x3_bf16_in": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "bk_selfplay_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(BkConfig), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "bk_selfplay_destroy": (None, [_P]),
     "bk_selfplay_reset": (C.c_int, [_P, C.c_uint32]),

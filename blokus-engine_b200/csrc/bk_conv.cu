@@ -20,7 +20,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
-#include <map>
+#include <stdlib.h>
 
 namespace {
 
@@ -61,6 +61,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -100,112 +112,148 @@ __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w 
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // Y = act(conv3x3(X) + bias [+ R]) on the padded NHWC layout; pad rows of Y are written as zeros.
+// Persistent: cluster c computes tile groups c, c + n_clusters, ...; CTA r of the cluster takes tile group*CS + r.
+// The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the TMA/MMA
+// main loop of tile i + 1.  The weight tile of a step is the same for every CTA: each CTA of a cluster fetches
+// 1/CS of it and TMA-multicasts that slice into all CS shared memories (L2 -> SM traffic per step drops from
+// 48 KB to 16 + 32/CS KB); a stage is recycled when the MMAs of ALL CTAs of the cluster have consumed it.
+template <int CS>
 __global__ void __launch_bounds__(192, 1)
 k_conv3x3_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-             int m_total, int relu) {
+             int m_total, int n_tiles, int steps_per_tap, int relu) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + kStages * kBytesStage;
     auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
     auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(kStages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * uint32_t(2 * kStages);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStages * kBytesStage + 8 * (2 * kStages + 1));
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * uint32_t(2 * kStages + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * uint32_t(2 * kStages + 2 + a); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStages * kBytesStage + 8 * (2 * kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBlockM;
+    const int steps = kTaps * steps_per_tap;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                  // peers' barriers are initialised before anyone multicasts
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_holder;
+    const int crank = CS > 1 ? int(cluster_ctarank()) : 0;
+    const int n_groups = (n_tiles + CS - 1) / CS;
+    const int first_group = int(blockIdx.x) / CS, group_stride = int(gridDim.x) / CS;
+    constexpr uint16_t kMcMask = uint16_t((1u << CS) - 1u);
+    constexpr uint32_t kSliceRows = kBlockN / CS, kSliceBytes = kBytesB / CS;
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int ks = 0; ks < kSteps; ++ks) {
-                const int s = ks % kStages;
-                const uint32_t ph = uint32_t(ks / kStages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), kBytesStage);
-                const int tap = ks / kStepsPerTap, kc = ks % kStepsPerTap;
-                const int shift = (tap / 3 - 1) * kPadDim + (tap % 3 - 1);
-                const uint32_t a_dst = smem_base + uint32_t(s) * kBytesStage;
-                tma_load_2d(a_dst, &map_x, full_bar(s), kc * kBlockK, m0 + shift);
-                tma_load_2d(a_dst + kBytesA, &map_w, full_bar(s), kc * kBlockK, tap * kBlockN);
+            uint32_t it = 0;                                           // pipeline step counter across tiles
+            for (int grp = first_group; grp < n_groups; grp += group_stride) {
+                const int m0 = (grp * CS + crank) * kBlockM;
+                for (int ks = 0; ks < steps; ++ks, ++it) {
+                    const int s = int(it % kStages);
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), kBytesStage);
+                    const int tap = ks / steps_per_tap, kc = ks - tap * steps_per_tap;
+                    const int shift = (tap / 3 - 1) * kPadDim + (tap % 3 - 1);
+                    const uint32_t a_dst = smem_base + uint32_t(s) * kBytesStage;
+                    tma_load_2d(a_dst, &map_x, full_bar(s), kc * kBlockK, m0 + shift);
+                    if (CS == 1) tma_load_2d(a_dst + kBytesA, &map_w, full_bar(s), kc * kBlockK, tap * kBlockN);
+                    else tma_load_2d_mc(a_dst + kBytesA + uint32_t(crank) * kSliceBytes, &map_w, full_bar(s), kc * kBlockK,
+                                        tap * kBlockN + crank * int(kSliceRows), kMcMask);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int ks = 0; ks < kSteps; ++ks) {
-                const int s = ks % kStages;
-                const uint32_t ph = uint32_t(ks / kStages) & 1u;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, n_acc = 0;
+            for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+                const int acc = int(n_acc & 1u);
+                mbar_wait(tmem_empty_bar(acc), ((n_acc >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_base + uint32_t(s) * kBytesStage;
-                const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + kBytesA);
+                const uint32_t tmem_d = tmem_base + uint32_t(acc) * kTmemCols;
+                for (int ks = 0; ks < steps; ++ks, ++it) {
+                    const int s = int(it % kStages);
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_base + uint32_t(s) * kBytesStage;
+                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + kBytesA);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)       // 32 bytes (16 bf16) further along K = +2 in 16-byte units
-                    umma_f16(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), (ks > 0 || k > 0) ? 1u : 0u);
-                umma_commit(empty_bar(s));                    // frees the stage when these MMAs have read it
+                    for (int k = 0; k < kBlockK / 16; ++k)   // 32 bytes (16 bf16) further along K = +2 in 16-byte units
+                        umma_f16(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), (ks > 0 || k > 0) ? 1u : 0u);
+                    if (CS == 1) umma_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+                    else umma_commit_mc(empty_bar(s), kMcMask);   // ... in every CTA of the cluster
+                }
+                umma_commit(tmem_full_bar(acc));              // accumulator complete
             }
-            umma_commit(tmem_full_bar);                       // accumulator complete
         }
     } else {
-        mbar_wait(tmem_full_bar, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int wq = warp & 3;                              // TMEM lane quarter this warp may read
-        const int m = m0 + wq * 32 + lane;
-        const int pos = m % kPadImage;
-        const bool live = m < m_total;
-        const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
-        uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
-        const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
+        uint32_t n_acc = 0;
+        for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+            const int acc = int(n_acc & 1u);
+            mbar_wait(tmem_full_bar(acc), (n_acc >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = (grp * CS + crank) * kBlockM + wq * 32 + lane;
+            const int pos = m % kPadImage;
+            const bool live = m < m_total;
+            const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
+            uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
+            const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
 #pragma unroll 1
-        for (int cc = 0; cc < kBlockN / 32; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(cc * 32), v);
-            if (!live) continue;
-            uint32_t packed[16];
-            if (pad) {
+            for (int cc = 0; cc < kBlockN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc) * kTmemCols + uint32_t(cc * 32), v);
+                if (!live) continue;
+                uint32_t packed[16];
+                if (pad) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) packed[j] = 0u;
-            } else {
-                uint4 r4[4];
-                if (rrow) {
+                    for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                } else {
+                    uint4 r4[4];
+                    if (rrow) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                        for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                    }
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
+                        float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
+                        if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
+                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        packed[j] = pack_bf16(a, b);
+                    }
                 }
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
-                    float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
-                    if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
-                    if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                    packed[j] = pack_bf16(a, b);
-                }
+                for (int q = 0; q < 4; ++q)
+                    orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            // this warp is done reading the accumulator: hand it back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(acc)) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                  // nobody leaves while a peer may still signal its barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
     }
 }
 
@@ -224,12 +272,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows][256] bf16 matrix, box = 64 channels x box_rows rows, 128B swizzle, zero fill outside
-int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+// [rows][cols] bf16 matrix, box = 64 channels x box_rows rows, 128B swizzle, zero fill outside
+int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return bk_fail(BK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t dims[2] = {kChannels, rows};
-    const cuuint64_t strides[1] = {kChannels * 2};
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
     const cuuint32_t box[2] = {kBlockK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -242,28 +290,65 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_row
 }  // namespace
 #endif  // BK_WARP_EMU
 
-extern "C" int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual,
-                               void* dev_y, int batch, int relu, void* cuda_stream) {
+static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual, void* dev_y,
+                       int batch, int in_channels, int relu, void* cuda_stream) {
 #ifdef BK_WARP_EMU
-    (void)dev_x; (void)dev_w; (void)dev_bias; (void)dev_residual; (void)dev_y; (void)batch; (void)relu; (void)cuda_stream;
+    (void)dev_x; (void)dev_w; (void)dev_bias; (void)dev_residual; (void)dev_y; (void)batch; (void)in_channels; (void)relu; (void)cuda_stream;
     return bk_fail(BK_ERR_STATE, "bk_conv3x3_bf16: tensor-core kernel, not available in the CPU emulator build");
 #else
     if (!dev_x || !dev_w || !dev_bias || !dev_y || batch <= 0) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: bad argument");
-    static bool attr_set = false;
-    if (!attr_set) {
-        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-        attr_set = true;
+    if (in_channels <= 0 || in_channels > kChannels || in_channels % kBlockK) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: in_channels must be 64, 128, 192 or 256");
+    static int n_sm = 0;
+    static int cluster = 2;
+    if (!n_sm) {
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+        if (const char* e = getenv("BK_CONV_CLUSTER")) cluster = atoi(e);
+        if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+        int dev = 0;
+        BK_CUDA(cudaGetDevice(&dev));
+        BK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     const int m_total = batch * kPadImage;
     CUtensorMap map_x, map_w;
-    int rc = make_map(&map_x, dev_x, uint64_t(m_total), kBlockM);
+    int rc = make_map(&map_x, dev_x, uint64_t(in_channels), uint64_t(m_total), kBlockM);
     if (rc) return rc;
-    rc = make_map(&map_w, dev_w, uint64_t(kTaps) * kBlockN, kBlockN);
+    rc = make_map(&map_w, dev_w, uint64_t(in_channels), uint64_t(kTaps) * kBlockN, uint32_t(kBlockN / cluster));
     if (rc) return rc;
     const int tiles = (m_total + kBlockM - 1) / kBlockM;
-    k_conv3x3_tc<<<tiles, 192, kSmemBytes, static_cast<cudaStream_t>(cuda_stream)>>>(
-        map_x, map_w, dev_bias, static_cast<const __nv_bfloat16*>(dev_residual), static_cast<__nv_bfloat16*>(dev_y), m_total, relu);
+    const int groups = (tiles + cluster - 1) / cluster;
+    int n_clusters = n_sm / cluster;
+    if (groups < n_clusters) n_clusters = groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(n_clusters * cluster));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = static_cast<cudaStream_t>(cuda_stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(dev_residual);
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dev_y);
+    const int spt = in_channels / kBlockK;
+    if (cluster == 1) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<1>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    else if (cluster == 2) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<2>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    else BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<4>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     BK_CUDA(cudaGetLastError());
     return BK_OK;
 #endif
+}
+
+extern "C" int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual,
+                               void* dev_y, int batch, int relu, void* cuda_stream) {
+    return conv_launch(dev_x, dev_w, dev_bias, dev_residual, dev_y, batch, 256, relu, cuda_stream);
+}
+
+extern "C" int bk_conv3x3_bf16_in(const void* dev_x, const void* dev_w, const float* dev_bias, void* dev_y, int batch,
+                                  int in_channels, int relu, void* cuda_stream) {
+    return conv_launch(dev_x, dev_w, dev_bias, nullptr, dev_y, batch, in_channels, relu, cuda_stream);
 }

@@ -250,6 +250,11 @@ int bk_selfplay_last_kernel_ms(bk_selfplay* sp, float* ms_out);
  * relu != 0 applies ReLU.  The kernel is enqueued on cuda_stream (a cudaStream_t passed as void*). */
 int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual,
                     void* dev_y, int batch, int relu, void* cuda_stream);
+/* Same kernel for a narrower input (model/resnet.py:51, Conv2d(5, 256, 3) with the 5 planes zero-extended to 64
+ * channels): x bf16 [batch*441][in_channels], w bf16 [9][256][in_channels], in_channels in {64, 128, 192, 256};
+ * y bf16 [batch*441][256]. */
+int bk_conv3x3_bf16_in(const void* dev_x, const void* dev_w, const float* dev_bias, void* dev_y, int batch,
+                       int in_channels, int relu, void* cuda_stream);
 
 #ifdef __cplusplus
 }

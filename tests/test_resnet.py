@@ -74,3 +74,40 @@ def test_gpu_selfplay_with_resnet_config4_shape(cuda_lib, orc):
     assert all(len(h) == 6 for h in sp.env.history())
     c = sp.counters()
     assert c["sims"] == 64 * 6 * 48
+
+
+@pytest.mark.gpu
+def test_tensor_core_trunk_matches_torch_model(cuda_lib):
+    """the hand-written tcgen05 trunk against the same ResNet(width 256) evaluated by PyTorch in
+    fp32.  bf16 operands / bf16 activations between layers: tolerance 3e-2 absolute on the softmax outputs (the same
+    bound as the cuDNN bf16 path above), and each convolution alone within bf16 rounding of an fp32 reference."""
+    import torch.nn.functional as F
+    from blokus_self_play.resnet import ResNet, LeafEvaluator
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator, to_padded_nhwc, from_padded_nhwc, conv3x3, fold_conv_bn
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    # one convolution, fused residual + ReLU, odd batch (tail tile) — fp32 reference on bf16-rounded operands
+    B = 5
+    x = torch.relu(torch.randn(B, 256, 20, 20, device=dev))
+    r = torch.relu(torch.randn(B, 256, 20, 20, device=dev))
+    w = torch.randn(256, 256, 3, 3, device=dev) * 0.02
+    b = torch.randn(256, device=dev) * 0.1
+    ref = torch.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1) + r.bfloat16().float())
+    w9 = w.bfloat16().permute(2, 3, 0, 1).reshape(9, 256, 256).contiguous()
+    y = conv3x3(to_padded_nhwc(x), w9, b.contiguous(), to_padded_nhwc(r), True, B, lib=cuda_lib)
+    got = from_padded_nhwc(y, B)
+    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    pad = y.reshape(B, 21, 21, 256)
+    assert pad[:, 20].abs().max().item() == 0 and pad[:, :, 20].abs().max().item() == 0
+    # whole evaluator
+    model = ResNet(3, 256).to(dev).eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.6, 1.4); m.weight.uniform_(0.6, 1.4); m.bias.normal_(0, 0.1)
+    z = np.load(GOLD)
+    planes = torch.from_numpy(z["planes"]).to(dev)
+    p_ref, v_ref = LeafEvaluator(model)(planes)
+    p_tc, v_tc = TensorCoreLeafEvaluator(model, lib=cuda_lib)(planes)
+    assert (p_tc - p_ref).abs().max().item() <= 3e-2 and (v_tc - v_ref).abs().max().item() <= 3e-2
+    assert torch.all(p_tc[planes[:, 4].reshape(len(planes), -1) == 0] == 0)

@@ -16,10 +16,16 @@ ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--blocks", type=int, default=20)
 ap.add_argument("--width", type=int, default=256)
 ap.add_argument("--fp32", action="store_true")
+ap.add_argument("--tc", action="store_true", help="hand-written tcgen05 trunk (bk_conv3x3_bf16) instead of cuDNN")
 a = ap.parse_args()
 torch.manual_seed(20261018)
 dev = torch.device("cuda", 0)
-ev = LeafEvaluator(ResNet(a.blocks, a.width).to(dev), bf16=not a.fp32)
+model = ResNet(a.blocks, a.width).to(dev)
+if a.tc:
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    ev = TensorCoreLeafEvaluator(model)
+else:
+    ev = LeafEvaluator(model, bf16=not a.fp32)
 cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03, exploration_fraction=0.25, seed=1)
 sp = SelfPlay(a.games, cfg)
 sp.set_stream(torch.cuda.current_stream(dev).cuda_stream)
@@ -47,10 +53,10 @@ peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.ex
 tot = (t_eval + t_tree) * 1e-3
 print(json.dumps({
     "metric": "mcts_leaf_evals_per_sec_resnet", "value": evals / tot, "unit": "sims/s",
-    "config": f"configs[3]: {a.games} games, 800 sims/move, ResNet({a.blocks},{a.width}) random init, {'fp32' if a.fp32 else 'bf16 autocast, channels_last'}, "
+    "config": f"configs[3]: {a.games} games, 800 sims/move, ResNet({a.blocks},{a.width}) random init, {'hand-written tcgen05 convolutions (bf16 operands, f32 accumulate in TMEM)' if a.tc else ('fp32' if a.fp32 else 'bf16 autocast, channels_last')}, "
               f"eval mode; {a.rounds} lockstep evaluator rounds of the first ply timed",
     "ms_per_round": 1e3 * tot / a.rounds, "ms_eval": t_eval / a.rounds, "ms_tree_kernels": t_tree / a.rounds,
-    "evaluator": "PyTorch/cuDNN (library model; SURVEY §8f row f2 is the hand-written tcgen05 version)",
+    "evaluator": ("bk_conv3x3_bf16 (hand-written tcgen05/TMEM/TMA) for the input and the 40 trunk convolutions; 1x1 heads as one matmul; head arithmetic in PyTorch") if a.tc else "PyTorch/cuDNN (library model)",
     "roofline": {"bound": "tensor", "achieved": flops_per_leaf * evals / (t_eval * 1e-3) / 1e12, "peak": peaks.get("bf16_tflops_sustained"),
                  "unit": "TFLOP/s", "frac": flops_per_leaf * evals / (t_eval * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0),
                  "flops_per_leaf": flops_per_leaf, "note": "evaluator time only; the tree kernels add ms_tree_kernels per round"},
