@@ -144,6 +144,31 @@ def mcts_measure(local_rank: int, rank: int, plies: int):
     return out
 
 
+def leaf_eval_measure(local_rank: int, rounds: int = 10, warmup: int = 3) -> dict:
+    """BASELINE.json configs[3] building block: one evaluator round = ResNet(20,256) forward on 1024 leaves.
+    Hand-written tcgen05 trunk (bk_conv3x3_bf16) and, beside it, the PyTorch/cuDNN bf16 path."""
+    import torch
+    from blokus_self_play.resnet import ResNet, LeafEvaluator
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(SEED)
+    model = ResNet(20, 256).to(dev)
+    planes = (torch.rand((MCTS_GAMES, 5, 20, 20), device=dev) < 0.15).float()
+    out = {}
+    for name, ev in (("tcgen05", TensorCoreLeafEvaluator(model)), ("cudnn_bf16", LeafEvaluator(model, bf16=True))):
+        for _ in range(warmup):
+            ev(planes)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rounds):
+            ev(planes)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name] = e0.elapsed_time(e1) / rounds
+    return out
+
+
 def mcts_cpu_baseline(target_seconds: float = 10.0) -> dict:
     from oracle import oracle as orc
     thr = host_threads()
@@ -303,6 +328,7 @@ def main() -> int:
 
     # ---- secondary metric: MCTS sims/s (configs[2]) -------------------------------------------------
     mcts = None
+    leaf = None
     if not args.no_mcts:
         batch.close()
         del flush
@@ -310,6 +336,7 @@ def main() -> int:
         barrier()
         mcts = mcts_measure(local_rank, rank, args.mcts_plies)
         barrier()
+        leaf = leaf_eval_measure(local_rank) if rank == 0 else None
 
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
     stats = torch.tensor([region_ms, e2e_s, kernel_ms, mcts["kernel_ms"] if mcts else 0.0], dtype=torch.float64, device="cuda")
@@ -379,6 +406,20 @@ def main() -> int:
                 "int_roofline": {"achieved": mcts_lane_ops / world / (mcts_ms * 1e-3), "peak": int_peak, "unit": "lane-ops/s",
                                  "frac": mcts_lane_ops / world / (mcts_ms * 1e-3) / int_peak},
                 "child_entries_created": mcts_entries,
+            }
+        if leaf:
+            flops = 18883996800.0 * MCTS_GAMES
+            line["gpu_launches"] += 41 * 13
+            line["extra"]["leaf_eval"] = {
+                "metric": "resnet20x256_leaf_evals_per_sec", "value": MCTS_GAMES / (leaf["tcgen05"] * 1e-3), "unit": "leaves/s",
+                "config": "configs[3] building block: ResNet(20,256) random init, eval mode, 1024 leaves per round, one GPU; "
+                          "hand-written tcgen05/TMEM/TMA convolutions (bk_conv3x3_bf16), bf16 operands, f32 accumulate",
+                "ms_per_round": leaf["tcgen05"], "cudnn_bf16_ms_per_round": leaf["cudnn_bf16"],
+                "speedup_vs_cudnn_bf16": leaf["cudnn_bf16"] / leaf["tcgen05"],
+                "roofline": {"bound": "tensor", "achieved": flops / (leaf["tcgen05"] * 1e-3) / 1e12,
+                             "peak": peaks.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                             "frac": flops / (leaf["tcgen05"] * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0),
+                             "traffic": None, "note": "useful FLOPs (400 positions/image); the padded 21x21 layout executes 10 % more"},
             }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()

@@ -111,3 +111,31 @@ def test_tensor_core_trunk_matches_torch_model(cuda_lib):
     p_tc, v_tc = TensorCoreLeafEvaluator(model, lib=cuda_lib)(planes)
     assert (p_tc - p_ref).abs().max().item() <= 3e-2 and (v_tc - v_ref).abs().max().item() <= 3e-2
     assert torch.all(p_tc[planes[:, 4].reshape(len(planes), -1) == 0] == 0)
+
+
+@pytest.mark.gpu
+def test_gpu_selfplay_with_tcgen05_evaluator(cuda_lib, orc):
+    """Config 4 in miniature on the hand-written evaluator: ResNet(2,256) leaf evaluation by tcgen05 convolutions
+    inside the external-evaluator protocol; tree invariants hold and the first root's priors follow the network."""
+    from blokus_self_play import SelfPlay, Config
+    from blokus_self_play.resnet import ResNet, LeafEvaluator
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    torch.manual_seed(11)
+    model = ResNet(2, 256).cuda()
+    cfg = Config(sims_per_move=32, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                 exploration_fraction=0.0, seed=3)          # no noise: priors are the network's softmax-of-softmax
+    sp = SelfPlay(48, cfg, lib=cuda_lib)
+    info = sp.run_evaluator(TensorCoreLeafEvaluator(model, lib=cuda_lib), max_plies=3)
+    assert info["plies"] == 3
+    for recs in sp.policy_records():
+        assert len(recs) == 3
+        for tiles, visits in recs:
+            assert int(visits.sum()) == 32 and np.all(np.diff(tiles) > 0)
+    # priors of the last root against the fp32 PyTorch evaluator on the same position
+    ref = SelfPlay(48, cfg, lib=cuda_lib)
+    ref.run_evaluator(LeafEvaluator(model), max_plies=1)
+    tc = SelfPlay(48, cfg, lib=cuda_lib)
+    tc.run_evaluator(TensorCoreLeafEvaluator(model, lib=cuda_lib), max_plies=1)
+    for a, b in zip(ref.last_root(), tc.last_root()):
+        assert np.array_equal(a["tile"], b["tile"])
+        assert np.allclose(a["prior"], b["prior"], atol=2e-3)

@@ -11,6 +11,18 @@ if what == "playout":
         b.reset()
         r = b.playout(seed=k)
     print("playout", r["total_steps"], r["kernel_ms"])
+elif what == "conv":
+    import torch
+    from blokus_self_play.tc_resnet import to_padded_nhwc, conv3x3
+    dev = torch.device("cuda", 0)
+    xp = to_padded_nhwc(torch.relu(torch.randn(1024, 256, 20, 20, device=dev)))
+    w9 = (torch.randn(9, 256, 256, device=dev) * 0.02).to(torch.bfloat16)
+    bias = torch.zeros(256, device=dev)
+    out = torch.empty_like(xp)
+    for _ in range(4):
+        conv3x3(xp, w9, bias, xp, True, 1024, out=out)
+    torch.cuda.synchronize()
+    print("conv done")
 else:
     cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
                  exploration_fraction=0.25, seed=1)
