@@ -111,16 +111,7 @@ __global__ void k_legal_rows(const BkState* __restrict__ states, uint32_t* __res
 // ---- host side --------------------------------------------------------------------------------------
 static int grid_for(int n, int warps) { return (n + warps - 1) / warps; }
 
-int bk_env_alloc(int n_games, int device, cudaStream_t stream, bk_env** out) {
-    if (n_games <= 0 || !out) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_create: n_games must be > 0");
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-        return bk_fail(BK_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
-    if (device < 0 || device >= count) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_create: bad device index");
-    BK_CUDA(cudaSetDevice(device));
-    bk_env* e = new bk_env();
-    e->n = n_games;
-    e->device = device;
+static int env_alloc_into(bk_env* e, int n_games, cudaStream_t stream) {
     if (stream) { e->stream = stream; e->borrowed = true; }
     else BK_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     BK_CUDA(cudaMalloc(&e->d_states, sizeof(BkState) * size_t(n_games)));
@@ -138,6 +129,21 @@ int bk_env_alloc(int n_games, int device, cudaStream_t stream, bk_env** out) {
     BK_CUDA(cudaEventCreate(&e->ev1));
     BK_CUDA(cudaEventCreate(&e->uev[0]));
     BK_CUDA(cudaEventCreate(&e->uev[1]));
+    return BK_OK;
+}
+
+int bk_env_alloc(int n_games, int device, cudaStream_t stream, bk_env** out) {
+    if (n_games <= 0 || !out) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_create: n_games must be > 0");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return bk_fail(BK_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+    if (device < 0 || device >= count) return bk_fail(BK_ERR_INVALID_ARG, "bk_env_create: bad device index");
+    BK_CUDA(cudaSetDevice(device));
+    bk_env* e = new bk_env();
+    e->n = n_games;
+    e->device = device;
+    const int rc = env_alloc_into(e, n_games, stream);
+    if (rc) { bk_env_destroy(e); return rc; }       // nothing leaks when an allocation fails half way
     *out = e;
     return BK_OK;
 }

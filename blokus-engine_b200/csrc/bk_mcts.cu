@@ -195,6 +195,8 @@ static int sp_check_errors(bk_selfplay* sp) {
     return BK_OK;
 }
 
+static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_game_id, uint32_t max_children_per_game);
+
 extern "C" {
 
 int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t first_game_id,
@@ -211,6 +213,16 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     sp->first_id = first_game_id;
     int rc = bk_env_create(n_games, device, &sp->env);
     if (rc) { delete sp; return rc; }
+    rc = selfplay_alloc(sp, cfg, first_game_id, max_children_per_game);
+    if (rc) { bk_selfplay_destroy(sp); return rc; }  // e.g. cudaMalloc of the pools failed: release what exists
+    *out = sp;
+    return BK_OK;
+}
+
+}  // extern "C"
+
+static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_game_id, uint32_t max_children_per_game) {
+    const int n_games = sp->n;
     BkSearchCfg& d = sp->dcfg;
     d.sims = cfg->sims_per_move;
     d.sample_moves = cfg->sample_moves;
@@ -257,9 +269,10 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     d.prior_tab = sp->d_prior;
     BK_CUDA(cudaEventCreate(&sp->ev0));
     BK_CUDA(cudaEventCreate(&sp->ev1));
-    *out = sp;
     return BK_OK;
 }
+
+extern "C" {
 
 void bk_selfplay_destroy(bk_selfplay* sp) {
     if (!sp) return;
