@@ -72,8 +72,33 @@ struct BkWarpSmem {
     float e[400];
     uint16_t tile[400];
     uint32_t path[BK_PATH_CAP];
+    uint32_t path_n[BK_PATH_CAP];   // visits / value_sum of the path entries as the select read them
+    uint32_t path_w[BK_PATH_CAP];   // (valid only inside one kernel: the backup then needs no reload)
     uint8_t path_tp[BK_PATH_CAP];
 };
+
+// Optional streaming (evict-first) stores for what an expansion writes (-DBK_STREAM_STORES): of the ~10 k
+// child entries and 800 node states a move tree creates only a few are ever read again.  Measured on B200
+// (1024 games, 800 sims, complete games): 1297 ms with, 1283 ms without — within noise, so it is off.
+#if defined(BK_WARP_EMU) || !defined(BK_STREAM_STORES)
+#define BK_ST_STREAM(ptr, v) (*(ptr) = (v))
+#else
+#define BK_ST_STREAM(ptr, v) __stcs((ptr), (v))
+#endif
+
+__device__ __forceinline__ void bk_store_stream(BkState* __restrict__ s, int lane, const BkRegs& G) {
+    if (lane < 20) {
+        BK_ST_STREAM(reinterpret_cast<uint4*>(s->own) + lane, make_uint4(G.o0, G.o1, G.o2, G.o3));
+        BK_ST_STREAM(&s->legal[lane], G.legal);
+    }
+    if (lane == 0) {
+        BK_ST_STREAM(reinterpret_cast<uint4*>(s->pieces), make_uint4(G.pc0, G.pc1, G.pc2, G.pc3));
+        BK_ST_STREAM(reinterpret_cast<uint4*>(&s->meta), make_uint4(G.meta, G.lastlens, G.t01, G.t23));
+        BK_ST_STREAM(&s->ply, G.ply);
+        BK_ST_STREAM(reinterpret_cast<uint4*>(&s->alive), make_uint4(G.alive, G.tw0, G.tw1, G.tw2));
+    }
+    BK_ST_STREAM(&s->smask[lane], (unsigned short)(G.smask));
+}
 
 // f32 exp as the oracle defines it: exp in f64, rounded once to f32 (see oracle/mcts_oracle.hpp exp_f32)
 __device__ __forceinline__ float bk_exp_f32(float x) { return float(exp(double(x))); }
@@ -95,9 +120,12 @@ __device__ __forceinline__ int bk_frame_index(int r, int c, int cur) {
 // policy > 0 when a policy is given), priors exp(p)/sum exp(p) summed sequentially in ascending order.
 // Writes state L to node slot `hdr.n_nodes` and returns that node id, or BK_NODE_NONE when the state
 // yields no child (the node then stays unexpanded, as in the reference) or a pool overflowed.
+struct BkBlock { uint32_t off, n; };   // child block of the node an expansion created
+
 __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                    const BkRegs& L, const float* policy, int lane, BkWarpSmem& sm,
-                                                   BkSpCounters& ctr) {
+                                                   BkSpCounters& ctr, BkBlock& blk) {
+    blk.off = 0u; blk.n = 0u;
     const int cur = bk_cur(L);
     // per-lane pass over this row's legal tiles
     uint32_t m = L.legal;
@@ -147,15 +175,16 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
     const float stub_prior = cfg.prior_tab[n];
     for (int i = lane; i < n; i += 32) {
         const float pr = policy ? __fdiv_rn(sm.e[i], total) : stub_prior;
-        tr.S[off + i] = make_uint4(0u, 0u, __float_as_uint(pr), uint32_t(sm.tile[i]));
-        tr.X[off + i] = make_uint4(0u, 0u, BK_NODE_NONE, 0u);
+        BK_ST_STREAM(&tr.S[off + i], make_uint4(0u, 0u, __float_as_uint(pr), uint32_t(sm.tile[i])));
+        BK_ST_STREAM(&tr.X[off + i], make_uint4(0u, 0u, BK_NODE_NONE, 0u));
     }
     BkState* ns = &tr.nodes[id];
-    bk_store(ns, lane, L);
-    if (lane == 0) { ns->pad[0] = off; ns->pad[1] = uint32_t(n); }
+    bk_store_stream(ns, lane, L);
+    if (lane == 0) { BK_ST_STREAM(&ns->pad[0], off); BK_ST_STREAM(&ns->pad[1], uint32_t(n)); }
     hd.n_entries += uint32_t(n);
     hd.n_nodes += 1u;
     if (lane == 0) { ctr.entries += uint32_t(n); ctr.nodes += 1u; }
+    blk.off = off; blk.n = uint32_t(n);
     __syncwarp();
     return id;
 }
@@ -163,13 +192,12 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
 // after evaluate(): the leaf entry remembers the seat to move at it (node.to_play, simulation.rs:78) and,
 // if it got children, its child block and node id
 __device__ __forceinline__ void bk_tree_link(const BkTree& tr, uint32_t entry, int tile, uint32_t id, int to_play,
-                                             int lane) {
+                                             const BkBlock& blk, int lane) {
     if (lane == 0) {
         uint32_t tn = uint32_t(tile) | (uint32_t(to_play) << 18);
         if (id != BK_NODE_NONE) {
-            const BkState* ns = &tr.nodes[id];
-            tn |= (ns->pad[1] << 9) | (1u << 20);
-            tr.X[entry].y = ns->pad[0];
+            tn |= (blk.n << 9) | (1u << 20);
+            tr.X[entry].y = blk.off;
             tr.X[entry].z = id;
         }
         tr.S[entry].w = tn;
@@ -223,15 +251,30 @@ struct BkLeaf {
     bool ok;
 };
 
-// the selection loop of mcts() (simulation.rs:198-203) with select_child/ucb_score (:88-98,:135-147)
-__device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, int lane,
-                                                 BkWarpSmem& sm) {
+// Optional (-DBK_CHILD_PREFETCH): ask L2 for the child blocks of every expanded child of this level while
+// the scores are being computed.  Measured on B200: no gain (the kernel is bound by dependent issue
+// latency, not by L2 misses: profiles/r01_ab_mcts_variants.log), so it is off.
+__device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn, uint32_t off) {
+#if !defined(BK_WARP_EMU) && defined(BK_CHILD_PREFETCH)
+    if (BK_TN_EXPANDED(tn)) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tr.S + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tr.X + off));
+    }
+#else
+    (void)tr; (void)tn; (void)off;
+#endif
+}
+
+// the selection loop of mcts() (simulation.rs:198-203) with select_child/ucb_score (:88-98,:135-147).
+// `root` is the root's child block (kept in registers by the caller: no per-simulation reload).
+__device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
+                                                 const BkBlock& root, int lane, BkWarpSmem& sm) {
     BkLeaf lf;
     lf.ok = true;
     lf.parent = 0u; lf.entry = 0u; lf.tile = 0;
     uint32_t node = 0u;
-    uint32_t off = tr.nodes[0].pad[0];
-    int n = int(tr.nodes[0].pad[1]);
+    uint32_t off = root.off;
+    int n = int(root.n);
     uint32_t Np = hd.root_visits;
     int depth = 0;
     for (;;) {
@@ -239,7 +282,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         // next: ask L2 for its 5 lines now, one level of latency ahead.
         bk_prefetch_state(&tr.nodes[node], lane);
         const float F = cfg.ucb_tab[Np];
-        uint32_t wi, b_tn = 0u, b_n = 0u, b_off = 0u, b_node = 0u;
+        uint32_t wi, b_tn = 0u, b_n = 0u, b_w = 0u, b_off = 0u, b_node = 0u;
         if (n <= 32) {
             // one child per lane (the common case): score it, the last maximal child is the highest
             // lane holding the maximum (`>=` over ascending order, simulation.rs:141)
@@ -247,10 +290,11 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
             if (lane < n) {
                 const uint4 sv = tr.S[off + lane];
                 const uint4 xv = tr.X[off + lane];
+                bk_prefetch_block(tr, sv.w, xv.y);
                 const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));                         // simulation.rs:92-94
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));  // :95-97, Q cached
                 if (sc >= 0.0f) key = __float_as_uint(sc) + 1u;                                     // NaN / negative never wins
-                b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z;
+                b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z;
             }
             const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
             if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
@@ -263,7 +307,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
                 const uint4 xv = tr.X[off + i];
                 const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
-                if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_off = xv.y; b_node = xv.z; }
+                if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z; }
             }
             const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
             const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
@@ -274,7 +318,10 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         const uint32_t tn = __shfl_sync(BK_FULL, b_tn, src);
         if (depth >= BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; break; }
         const uint32_t e = off + wi;
-        if (lane == 0) { sm.path[depth] = e; sm.path_tp[depth] = uint8_t(BK_TN_TOPLAY(tn)); }
+        if (lane == src) {                                 // the winner's lane holds everything the backup needs
+            sm.path[depth] = e; sm.path_n[depth] = b_n; sm.path_w[depth] = b_w;
+            sm.path_tp[depth] = uint8_t(BK_TN_TOPLAY(tn));
+        }
         ++depth;
         if (!BK_TN_EXPANDED(tn)) {
             lf.parent = node;
@@ -293,14 +340,15 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
 }
 
 // backpropagate (simulation.rs:164-171): every entry on the path gets +1 visit and the value of the seat
-// to move AT that node (0 for a terminal / unexpanded leaf, node.rs:20)
+// to move AT that node (0 for a terminal / unexpanded leaf, node.rs:20).  The visit count and value sum
+// the select read are still current (one simulation in flight per game), so nothing is reloaded.
 __device__ __forceinline__ void bk_tree_backup(const BkTree& tr, int depth, const float (&val)[4], int lane,
                                                const BkWarpSmem& sm) {
     for (int d = lane; d < depth; d += 32) {
         const uint32_t e = sm.path[d];
         const int tp = int(sm.path_tp[d]);
-        const uint32_t nv = tr.S[e].x + 1u;                                                          // visits += 1
-        const float w = __fadd_rn(__uint_as_float(tr.X[e].x), bk_sel4f(tp, val[0], val[1], val[2], val[3]));
+        const uint32_t nv = sm.path_n[d] + 1u;                                                       // visits += 1
+        const float w = __fadd_rn(__uint_as_float(sm.path_w[d]), bk_sel4f(tp, val[0], val[1], val[2], val[3]));
         tr.X[e].x = __float_as_uint(w);                                                              // value_sum +=
         *reinterpret_cast<uint2*>(&tr.S[e]) = make_uint2(nv, __float_as_uint(__fdiv_rn(w, float(nv))));  // N, Q
     }
@@ -357,10 +405,11 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
 
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
 // evaluate (terminal payoff, or stub value + expansion), back up.
-__device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, int lane,
-                                            const BkTabs& tabs, BkWarpSmem& sm, BkCounters& gctr, BkSpCounters& ctr) {
+__device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
+                                            const BkBlock& root, int lane, const BkTabs& tabs, BkWarpSmem& sm,
+                                            BkCounters& gctr, BkSpCounters& ctr) {
     hd.root_visits += 1u;                                                        // simulation.rs:194
-    const BkLeaf lf = bk_tree_select(tr, hd, cfg, lane, sm);
+    const BkLeaf lf = bk_tree_select(tr, hd, cfg, root, lane, sm);
     if (!lf.ok) return;
     BkRegs L;
     bk_load(&tr.nodes[lf.parent], lane, L);
@@ -371,9 +420,10 @@ __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, c
     if (bk_terminal(L)) {
         bk_payoff(L, val);                                                       // simulation.rs:45-47
     } else {
-        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, nullptr, lane, sm, ctr);
+        BkBlock blk;
+        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, nullptr, lane, sm, ctr, blk);
         tp = bk_cur(L);                                                          // simulation.rs:78
-        bk_tree_link(tr, lf.entry, lf.tile, id, tp, lane);
+        bk_tree_link(tr, lf.entry, lf.tile, id, tp, blk, lane);
         val[0] = val[1] = val[2] = val[3] = cfg.stub_value;
     }
     if (lane == 0) sm.path_tp[lf.depth - 1] = uint8_t(tp);
@@ -401,9 +451,10 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
     int plies = 0;
     while (!bk_terminal(G) && (max_plies < 0 || plies < max_plies) && hd.err == 0u) {
         hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
-        bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr);                        // evaluate(root), :184
+        BkBlock root;
+        bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);                  // evaluate(root), :184
         bk_tree_noise(tr, cfg, game_id, G.ply, lane);                                  // :190
-        for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, lane, tabs, sm, gctr, ctr);
+        for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
         if (hd.err) break;
         const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
         const int p = bk_cur(G);
@@ -441,11 +492,16 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
 #define BK_PEND_LEAF 2u   // a leaf position waiting for the evaluator         (simulation.rs:206)
 #define BK_PEND_DONE 3u   // all simulations of this ply are done; waiting for bk_selfplay_end_ply
 
-__device__ __forceinline__ void bk_hdr_load(const BkSearchHdr* h, BkSearchHdr& hd, int lane, BkWarpSmem& sm) {
+__device__ __forceinline__ void bk_hdr_load(const BkSearchHdr* h, BkSearchHdr& hd, const BkTree& tr, int lane,
+                                            BkWarpSmem& sm) {
     hd.n_nodes = h->n_nodes; hd.n_entries = h->n_entries; hd.root_visits = h->root_visits; hd.sims_done = h->sims_done;
     hd.pend_kind = h->pend_kind; hd.pend_depth = h->pend_depth; hd.pend_parent = h->pend_parent; hd.pend_tile = h->pend_tile;
     hd.err = h->err; hd.pol_count = h->pol_count; hd.plies_searched = h->plies_searched; hd.pend_entry = h->pend_entry;
-    for (int d = lane; d < int(hd.pend_depth) && d < BK_PATH_CAP; d += 32) { sm.path[d] = h->path[d]; sm.path_tp[d] = h->path_tp[d]; }
+    for (int d = lane; d < int(hd.pend_depth) && d < BK_PATH_CAP; d += 32) {
+        const uint32_t e = h->path[d];
+        sm.path[d] = e; sm.path_tp[d] = h->path_tp[d];
+        sm.path_n[d] = tr.S[e].x; sm.path_w[d] = tr.X[e].x;    // what the select had read (nothing ran in between)
+    }
     __syncwarp();
 }
 
@@ -480,7 +536,7 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
                                            unsigned long long* counters, int g, int lane, const BkTabs& tabs,
                                            BkWarpSmem& sm) {
     BkSearchHdr hd;
-    bk_hdr_load(hdr_g, hd, lane, sm);
+    bk_hdr_load(hdr_g, hd, tr, lane, sm);
     if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF) return;
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
@@ -488,14 +544,17 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
     const float* pol = policy + size_t(g) * 400;
     BkRegs L;
     bk_load(&tr.nodes[hd.n_nodes], lane, L);            // the pending position (tentative node slot)
+    BkBlock root;
     if (hd.pend_kind == BK_PEND_ROOT) {
-        bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr);                            // evaluate(root), value dropped
+        bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, root);                      // evaluate(root), value dropped
         if (hd.n_nodes == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; }                         // reference: unwrap on None
         else bk_tree_noise(tr, cfg, game_id, L.ply, lane);
     } else {
-        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr);
+        root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
+        BkBlock blk;
+        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, blk);
         const int cur = bk_cur(L);
-        bk_tree_link(tr, hd.pend_entry, int(hd.pend_tile), id, cur, lane);
+        bk_tree_link(tr, hd.pend_entry, int(hd.pend_tile), id, cur, blk, lane);
         float val[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) val[i] = value[size_t(g) * 4 + ((i + 4 - cur) & 3)];   // value.rotate_right(cur)
@@ -509,7 +568,7 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
     hd.pend_depth = 0u;
     while (hd.sims_done < cfg.sims && hd.err == 0u) {
         hd.root_visits += 1u;
-        const BkLeaf lf = bk_tree_select(tr, hd, cfg, lane, sm);
+        const BkLeaf lf = bk_tree_select(tr, hd, cfg, root, lane, sm);
         if (!lf.ok) break;
         bk_load(&tr.nodes[lf.parent], lane, L);
         if (!bk_apply(L, lf.tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }
@@ -551,7 +610,7 @@ __device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __res
                                           uint32_t* pol_visits, unsigned long long* counters, int g, int lane,
                                           const BkTabs& tabs, BkWarpSmem& sm) {
     BkSearchHdr hd;
-    bk_hdr_load(hdr_g, hd, lane, sm);
+    bk_hdr_load(hdr_g, hd, tr, lane, sm);
     if (hd.pend_kind != BK_PEND_DONE) return;
     BkRegs G;
     bk_load(&states[g], lane, G);
