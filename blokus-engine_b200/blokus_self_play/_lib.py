@@ -26,6 +26,9 @@ PLAYOUT_HASH = 1
 PLAYOUT_MIN_TILE = 2
 PLAYOUT_MAX_TILE = 4
 
+MODE_SKIP_FORCED = 1
+MODE_FORCE_MULTI_LEAF = 2
+
 
 class BkError(RuntimeError):
     """A negative bk_status; `.code` holds it, the text is bk_last_error() (cf. Err(String))."""
@@ -100,6 +103,7 @@ _SIGNATURES = {
     "bk_selfplay_expand_backup": (C.c_int, [_P, _P, _P, _P]),
     "bk_selfplay_end_ply": (C.c_int, [_P]),
     "bk_selfplay_set_stream": (C.c_int, [_P, _P]),
+    "bk_selfplay_set_mode": (C.c_int, [_P, C.c_uint32, C.c_int]),
     "bk_selfplay_live_games": (C.c_int, [_P, _P]),
     "bk_selfplay_env": (_P, [_P]),
     "bk_selfplay_results": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),

@@ -49,6 +49,8 @@ class SelfPlay:
         self.lib.check(self.lib.bk_selfplay_create(self.n, device, C.byref(self._cfg), first_game_id,
                                                    max_children_per_game, C.byref(h)))
         self._h = h
+        self.leaves_per_round = 1
+        self.mode = 0
         self.env = GameBatch(self.n, device=device, lib=self.lib, _handle=self.lib.bk_selfplay_env(self._h))
 
     def close(self):
@@ -71,6 +73,14 @@ class SelfPlay:
         """training_game() with the fixed-prior stub evaluator, on the device; returns kernel ms."""
         self.lib.check(self.lib.bk_selfplay_run_stub(self._h, max_plies))
         return self.last_kernel_ms()
+
+    def set_mode(self, flags: int = 0, leaves_per_round: int = 1) -> None:
+        """Opt-in throughput modes (bk_selfplay_set_mode): flags = MODE_SKIP_FORCED (single-legal-tile roots are
+        not searched; the training tuple is unchanged) and leaves_per_round K > 1 (K simulations per game in flight
+        per evaluator round, virtual loss; visit counts then differ from the reference's).  Defaults = exact mode."""
+        self.lib.check(self.lib.bk_selfplay_set_mode(self._h, int(flags), int(leaves_per_round)))
+        self.mode = int(flags)
+        self.leaves_per_round = int(leaves_per_round)
 
     # ---- external evaluator (simulation.rs:50-57 replaced by one device batch per round) ---------------
     def set_stream(self, cuda_stream: int) -> None:
@@ -98,10 +108,10 @@ class SelfPlay:
 
         evaluator(planes[n,5,20,20] float32) -> (policy[n,400] float32 in the mover's frame, value[n,4] float32
         in relative-seat order), exactly the contract of the reference's inference server
-        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch.
+        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch (n = games x leaves_per_round).
         xp="torch": CUDA tensors on this handle's device; xp="numpy": host arrays, valid only with the tests'
         CPU-emulator build of the library (where "device" memory is host memory)."""
-        n = self.n
+        n = self.n * self.leaves_per_round      # slot j of game g is row g * K + j; unused slots are zero planes
         if xp == "torch":
             import torch
             dev = torch.device("cuda", self.env.device)

@@ -21,6 +21,8 @@ struct bk_selfplay {
     BkState* d_nodes = nullptr;
     double* d_scratch = nullptr;
     BkSearchHdr* d_hdr = nullptr;
+    BkPend* d_pend = nullptr;         // [n][leaves_per_round], multi-leaf mode only
+    bool use_vl = false;
     uint32_t* d_pol_off = nullptr;    // [n][BK_HIST_CAP + 1]
     uint16_t* d_pol_tile = nullptr;   // [n][policy_cap]
     uint32_t* d_pol_visits = nullptr; // [n][policy_cap]
@@ -42,7 +44,7 @@ __global__ void k_sp_summary(const BkState* __restrict__ states, BkSummary* __re
 }
 
 struct BkPools {
-    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr;
+    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr; BkPend* pend;
     uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
 };
 
@@ -75,19 +77,29 @@ __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n) return;
-    kb_sp_begin(states, bk_tree_of(pl, cfg, g), &pl.hdr[g], g, lane);
+    kb_sp_begin(cfg, states, bk_tree_of(pl, cfg, g), &pl.hdr[g], g, lane);
 }
 
 // planes of every game's pending position, float32 [n][5][20][20]; counts pending games
-__global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, float* __restrict__ out, int32_t* __restrict__ pending) {
-    const int g = blockIdx.x;
+__global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* __restrict__ out,
+                            int32_t* __restrict__ pending) {
+    const int K = int(cfg.leaves_per_round);
+    const int g = blockIdx.x / K, j = blockIdx.x % K;   // game, leaf slot of the round (K = 1 in the exact mode)
     if (g >= n) return;
     const BkSearchHdr* h = &pl.hdr[g];
-    const bool pend = h->pend_kind == BK_PEND_ROOT || h->pend_kind == BK_PEND_LEAF;
-    float* o = out + size_t(g) * 2000;
+    bool pend = h->pend_kind == BK_PEND_ROOT || h->pend_kind == BK_PEND_LEAF;
+    uint32_t slot = h->n_nodes;                      // exact mode: the tentative node slot
+    if (vl) {
+        if (h->pend_kind == BK_PEND_ROOT) { pend = j == 0; slot = 0u; }
+        else if (h->pend_kind == BK_PEND_LEAF) {
+            pend = uint32_t(j) < h->pend_count;
+            if (pend) slot = pl.pend[size_t(g) * cfg.leaves_per_round + j].slot;
+        }
+    }
+    float* o = out + size_t(blockIdx.x) * 2000;
     if (pend) {
-        kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[h->n_nodes], o, threadIdx.x, blockDim.x);
-        if (threadIdx.x == 0) atomicAdd(pending, 1);
+        kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], o, threadIdx.x, blockDim.x);
+        if (threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
     } else {
         for (int e = threadIdx.x; e < 2000; e += blockDim.x) o[e] = 0.0f;
     }
@@ -111,6 +123,19 @@ k_sp_step(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* 
     const int g = blockIdx.x;
     if (g >= n) return;
     kb_sp_step(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], policy, value, counters, g, lane, tabs, wsm);
+}
+
+__global__ void __launch_bounds__(32)
+k_sp_step_vl(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* value, unsigned long long* counters) {
+    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ BkWarpSmem wsm;
+    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    kb_sp_step_vl(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], pl.pend + size_t(g) * cfg.leaves_per_round, policy, value,
+                  counters, g, lane, tabs, wsm);
 }
 
 __global__ void __launch_bounds__(32)
@@ -168,7 +193,7 @@ static float host_exp_f32(float x) { return float(std::exp(double(x))); }  // sa
 static BkPools pools_of(const bk_selfplay* sp) {
     BkPools p;
     p.S = sp->d_S; p.X = sp->d_X; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
-    p.hdr = sp->d_hdr; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
+    p.hdr = sp->d_hdr; p.pend = sp->d_pend; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
     return p;
 }
 
@@ -233,6 +258,8 @@ static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_
     d.max_nodes = cfg->sims_per_move + 2u;
     d.entry_cap = max_children_per_game ? max_children_per_game : (cfg->sims_per_move + 2u) * 128u;
     d.policy_cap = 32768u;
+    d.mode = 0u;
+    d.leaves_per_round = 1u;
     d.stub_value = 0.25f;
     const size_t ne = size_t(n_games) * d.entry_cap;
     BK_CUDA(cudaMalloc(&sp->d_S, sizeof(uint4) * ne));
@@ -282,6 +309,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
     cudaFree(sp->d_stage);
     cudaFree(sp->d_ply_off);
+    cudaFree(sp->d_pend);
     if (sp->ev0) cudaEventDestroy(sp->ev0);
     if (sp->ev1) cudaEventDestroy(sp->ev1);
     bk_env_destroy(sp->env);
@@ -297,6 +325,30 @@ int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id) {
     sp->dcfg.first_game_id = first_game_id;
     BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(sp->n), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(sp->n), sp->env->stream));
+    return BK_OK;
+}
+
+int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (flags & ~(BK_MODE_SKIP_FORCED | BK_MODE_FORCE_MULTI_LEAF))
+        return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_set_mode: unknown flag");
+    if (leaves_per_round < 1 || leaves_per_round > BK_MAX_LEAVES_PER_ROUND)
+        return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_set_mode: leaves_per_round must be in 1..32");
+    std::vector<BkSearchHdr> h(size_t(sp->n));
+    BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * h.size(), cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    for (const BkSearchHdr& x : h)
+        if (x.pend_kind != BK_PEND_NONE) return bk_fail(BK_ERR_STATE, "bk_selfplay_set_mode: a ply is in progress");
+    const bool vl = leaves_per_round > 1 || (flags & BK_MODE_FORCE_MULTI_LEAF);
+    if (vl && (!sp->d_pend || uint32_t(leaves_per_round) > sp->dcfg.leaves_per_round)) {
+        cudaFree(sp->d_pend);
+        sp->d_pend = nullptr;
+        BK_CUDA(cudaMalloc(&sp->d_pend, sizeof(BkPend) * size_t(sp->n) * size_t(leaves_per_round)));
+    }
+    sp->use_vl = vl;
+    sp->dcfg.mode = flags;
+    sp->dcfg.leaves_per_round = uint32_t(leaves_per_round);
     return BK_OK;
 }
 
@@ -343,7 +395,8 @@ int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending
     cudaStream_t st = sp->env->stream;
     int32_t* d_cnt = sp->env->d_i32 + 2;
     BK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t), st));
-    BK_LAUNCH(k_sp_planes, sp->n, 256, st, sp->dcfg, pools_of(sp), sp->n, dev_planes, d_cnt);
+BK_LAUNCH(k_sp_planes, sp->n * int(sp->dcfg.leaves_per_round), 256, st, sp->dcfg, pools_of(sp), sp->n,
+              sp->use_vl ? 1 : 0, dev_planes, d_cnt);
     BK_CUDA(cudaGetLastError());
     if (pending_out) {
         BK_CUDA(cudaMemcpyAsync(pending_out, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -358,7 +411,10 @@ int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const fl
     if (!dev_policy || !dev_value) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_expand_backup: null evaluator output");
     cudaStream_t st = sp->env->stream;
     BK_CUDA(cudaEventRecord(sp->ev0, st));
-    BK_LAUNCH(k_sp_step, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, dev_policy, dev_value, sp->d_counters);
+    if (sp->use_vl)
+        BK_LAUNCH(k_sp_step_vl, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, dev_policy, dev_value, sp->d_counters);
+    else
+        BK_LAUNCH(k_sp_step, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, dev_policy, dev_value, sp->d_counters);
     BK_CUDA(cudaEventRecord(sp->ev1, st));
     BK_CUDA(cudaGetLastError());
     if (pending_out) {

@@ -29,6 +29,12 @@
 #define BK_TN_NCHILD(tn) (((tn) >> 9) & 0x1FFu)
 #define BK_TN_TOPLAY(tn) (((tn) >> 18) & 3u)
 #define BK_TN_EXPANDED(tn) (((tn) >> 20) & 1u)
+#define BK_TN_PENDING(tn) (((tn) >> 21) & 1u)   // throughput mode: leaf selected, evaluator answer outstanding
+
+// opt-in throughput modes; 0 = the reference's exact behaviour
+#define BK_MODE_SKIP_FORCED_FLAG 1u   // a root position with exactly one legal tile is not searched
+#define BK_MODE_FORCE_VL_FLAG 2u      // run the multi-leaf code path even with one leaf per round (tests)
+#define BK_MAX_LEAVES_PER_ROUND 32
 
 #define BK_SP_ERR_ENTRY_CAP 1u
 #define BK_SP_ERR_PATH_CAP 2u
@@ -42,6 +48,7 @@ struct BkSearchCfg {
     uint64_t seed;
     uint32_t first_game_id;
     uint32_t max_nodes, entry_cap, policy_cap;
+    uint32_t mode, leaves_per_round;
     const float* ucb_tab;    // [sims + 2]: (ln((N + c_base + 1)/c_base) + c_init) * sqrt(N), host libm
     const float* prior_tab;  // [401]: stub prior for n children = e / (e + e + ... n times), f32 sequential
     float stub_value;        // 0.25
@@ -59,6 +66,14 @@ struct BkSearchHdr {
     uint32_t n_nodes, n_entries, root_visits, sims_done;
     uint32_t pend_kind, pend_depth, pend_parent, pend_tile;  // 0 none, 1 root, 2 leaf awaiting evaluator
     uint32_t err, pol_count, plies_searched, pend_entry;
+    uint32_t pend_count, forced_plies, rsv0, rsv1;   // multi-leaf mode: leaves outstanding; plies skipped as forced
+    uint32_t path[BK_PATH_CAP];
+    uint8_t path_tp[BK_PATH_CAP];
+};
+
+// one outstanding leaf of the multi-leaf (virtual loss) mode
+struct BkPend {
+    uint32_t depth, parent, tile, entry, slot, rsv[3];
     uint32_t path[BK_PATH_CAP];
     uint8_t path_tp[BK_PATH_CAP];
 };
@@ -124,8 +139,11 @@ struct BkBlock { uint32_t off, n; };   // child block of the node an expansion c
 
 __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                    const BkRegs& L, const float* policy, int lane, BkWarpSmem& sm,
-                                                   BkSpCounters& ctr, BkBlock& blk) {
+                                                   BkSpCounters& ctr, BkBlock& blk, uint32_t slot = BK_NODE_NONE,
+                                                   bool store_state = true) {
     blk.off = 0u; blk.n = 0u;
+    const bool own_slot = slot == BK_NODE_NONE;        // exact mode: the next free node; multi-leaf: reserved
+    const uint32_t id = own_slot ? hd.n_nodes : slot;
     const int cur = bk_cur(L);
     // per-lane pass over this row's legal tiles
     uint32_t m = L.legal;
@@ -162,7 +180,7 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
     }
     __syncwarp();
     if (n == 0) return BK_NODE_NONE;
-    if (hd.n_entries + uint32_t(n) > cfg.entry_cap || hd.n_nodes >= cfg.max_nodes) {
+    if (hd.n_entries + uint32_t(n) > cfg.entry_cap || id >= cfg.max_nodes) {
         hd.err |= BK_SP_ERR_ENTRY_CAP;
         return BK_NODE_NONE;
     }
@@ -171,7 +189,6 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
         for (int i = 0; i < n; ++i) total = __fadd_rn(total, sm.e[i]);  // simulation.rs:74, ascending order
     }
     const uint32_t off = hd.n_entries;
-    const uint32_t id = hd.n_nodes;
     const float stub_prior = cfg.prior_tab[n];
     for (int i = lane; i < n; i += 32) {
         const float pr = policy ? __fdiv_rn(sm.e[i], total) : stub_prior;
@@ -179,10 +196,10 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
         BK_ST_STREAM(&tr.X[off + i], make_uint4(0u, 0u, BK_NODE_NONE, 0u));
     }
     BkState* ns = &tr.nodes[id];
-    bk_store_stream(ns, lane, L);
+    if (store_state) bk_store_stream(ns, lane, L);
     if (lane == 0) { BK_ST_STREAM(&ns->pad[0], off); BK_ST_STREAM(&ns->pad[1], uint32_t(n)); }
     hd.n_entries += uint32_t(n);
-    hd.n_nodes += 1u;
+    if (own_slot) hd.n_nodes += 1u;
     if (lane == 0) { ctr.entries += uint32_t(n); ctr.nodes += 1u; }
     blk.off = off; blk.n = uint32_t(n);
     __syncwarp();
@@ -249,6 +266,7 @@ struct BkLeaf {
     int tile;
     int depth;        // path length (>= 1)
     bool ok;
+    bool collide;     // multi-leaf mode: the leaf is already waiting for the evaluator
 };
 
 // Optional (-DBK_CHILD_PREFETCH): ask L2 for the child blocks of every expanded child of this level while
@@ -267,10 +285,15 @@ __device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn,
 
 // the selection loop of mcts() (simulation.rs:198-203) with select_child/ucb_score (:88-98,:135-147).
 // `root` is the root's child block (kept in registers by the caller: no per-simulation reload).
+// VL (multi-leaf throughput mode): every entry on the way down gets its visit at once — a visit worth 0
+// until the value arrives, i.e. a virtual loss (Q = W / (N + 1)) that steers the next selections of the
+// same round elsewhere; the backup then only adds the value.  One warp owns the tree, so no atomics.
+template <bool VL>
 __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                  const BkBlock& root, int lane, BkWarpSmem& sm) {
     BkLeaf lf;
     lf.ok = true;
+    lf.collide = false;
     lf.parent = 0u; lf.entry = 0u; lf.tile = 0;
     uint32_t node = 0u;
     uint32_t off = root.off;
@@ -321,12 +344,18 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         if (lane == src) {                                 // the winner's lane holds everything the backup needs
             sm.path[depth] = e; sm.path_n[depth] = b_n; sm.path_w[depth] = b_w;
             sm.path_tp[depth] = uint8_t(BK_TN_TOPLAY(tn));
+            if (VL && !BK_TN_PENDING(tn)) {
+                const uint32_t nv = b_n + 1u;
+                *reinterpret_cast<uint2*>(&tr.S[e]) =
+                    make_uint2(nv, __float_as_uint(__fdiv_rn(__uint_as_float(b_w), float(nv))));
+            }
         }
         ++depth;
         if (!BK_TN_EXPANDED(tn)) {
             lf.parent = node;
             lf.entry = e;
             lf.tile = int(BK_TN_TILE(tn));
+            lf.collide = VL && BK_TN_PENDING(tn);
             break;
         }
         Np = __shfl_sync(BK_FULL, b_n, src);
@@ -403,13 +432,32 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
     return int(BK_TN_TILE(tr.S[off + uint32_t(pick)].w));
 }
 
+// write the single-child root of a forced ply: finish_ply then emits [(tile, sims)] and plays the tile
+__device__ __forceinline__ bool bk_forced_root(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, const BkRegs& G,
+                                               int lane) {
+    if (!(cfg.mode & BK_MODE_SKIP_FORCED_FLAG)) return false;
+    if (bk_legal_count(G.legal) != 1) return false;
+    const unsigned who = __ballot_sync(BK_FULL, G.legal != 0u);
+    const int row = __ffs(who) - 1;
+    const int tile = row * 20 + (__ffs(__shfl_sync(BK_FULL, G.legal, row)) - 1);
+    if (lane == 0) {
+        tr.S[0] = make_uint4(cfg.sims, 0u, __float_as_uint(1.0f), uint32_t(tile));
+        tr.X[0] = make_uint4(0u, 0u, BK_NODE_NONE, 0u);
+        tr.nodes[0].pad[0] = 0u; tr.nodes[0].pad[1] = 1u;
+    }
+    hd.n_nodes = 1u; hd.n_entries = 1u; hd.root_visits = cfg.sims; hd.sims_done = cfg.sims;
+    hd.forced_plies += 1u;
+    __syncwarp();
+    return true;
+}
+
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
 // evaluate (terminal payoff, or stub value + expansion), back up.
 __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                             const BkBlock& root, int lane, const BkTabs& tabs, BkWarpSmem& sm,
                                             BkCounters& gctr, BkSpCounters& ctr) {
     hd.root_visits += 1u;                                                        // simulation.rs:194
-    const BkLeaf lf = bk_tree_select(tr, hd, cfg, root, lane, sm);
+    const BkLeaf lf = bk_tree_select<false>(tr, hd, cfg, root, lane, sm);
     if (!lf.ok) return;
     BkRegs L;
     bk_load(&tr.nodes[lf.parent], lane, L);
@@ -445,16 +493,19 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
     hd.err = hdr_g->err;
     hd.pol_count = hdr_g->pol_count;
     hd.plies_searched = hdr_g->plies_searched;
+    hd.forced_plies = hdr_g->forced_plies;
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
     int plies = 0;
     while (!bk_terminal(G) && (max_plies < 0 || plies < max_plies) && hd.err == 0u) {
         hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
-        BkBlock root;
-        bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);                  // evaluate(root), :184
-        bk_tree_noise(tr, cfg, game_id, G.ply, lane);                                  // :190
-        for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
+        if (!bk_forced_root(tr, hd, cfg, G, lane)) {                                   // (opt-in shortcut, off by default)
+            BkBlock root;
+            bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);              // evaluate(root), :184
+            bk_tree_noise(tr, cfg, game_id, G.ply, lane);                              // :190
+            for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
+        }
         if (hd.err) break;
         const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
         const int p = bk_cur(G);
@@ -472,6 +523,7 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         hdr_g->n_entries = hd.n_entries;
         hdr_g->root_visits = hd.root_visits;
         hdr_g->sims_done = hd.sims_done;
+        hdr_g->forced_plies = hd.forced_plies;
         hdr_g->pend_kind = 0u;
     }
     const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
@@ -516,16 +568,22 @@ __device__ __forceinline__ void bk_hdr_store(BkSearchHdr* h, const BkSearchHdr& 
 }
 
 // start mcts() for one game: fresh tree, the root position becomes the pending leaf (tentative node 0)
-__device__ __forceinline__ void kb_sp_begin(const BkState* __restrict__ states, const BkTree& tr, BkSearchHdr* hdr_g, int g,
-                                            int lane) {
+__device__ __forceinline__ void kb_sp_begin(const BkSearchCfg& cfg, const BkState* __restrict__ states, const BkTree& tr,
+                                            BkSearchHdr* hdr_g, int g, int lane) {
     BkRegs G;
     bk_load(&states[g], lane, G);
     const bool live = !bk_terminal(G) && hdr_g->err == 0u;
-    if (live) bk_store(&tr.nodes[0], lane, G);
+    BkSearchHdr hd;
+    hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;
+    hd.forced_plies = hdr_g->forced_plies;
+    const bool forced = live && bk_forced_root(tr, hd, cfg, G, lane);      // opt-in shortcut, off by default
+    if (live && !forced) bk_store(&tr.nodes[0], lane, G);
     if (lane == 0) {
-        hdr_g->n_nodes = 0u; hdr_g->n_entries = 0u; hdr_g->root_visits = 0u; hdr_g->sims_done = 0u;
+        hdr_g->n_nodes = hd.n_nodes; hdr_g->n_entries = hd.n_entries; hdr_g->root_visits = hd.root_visits;
+        hdr_g->sims_done = hd.sims_done; hdr_g->forced_plies = hd.forced_plies;
         hdr_g->pend_depth = 0u; hdr_g->pend_parent = 0u; hdr_g->pend_tile = 0u; hdr_g->pend_entry = 0u;
-        hdr_g->pend_kind = live ? BK_PEND_ROOT : BK_PEND_NONE;
+        hdr_g->pend_count = 0u;
+        hdr_g->pend_kind = !live ? BK_PEND_NONE : (forced ? BK_PEND_DONE : BK_PEND_ROOT);
     }
 }
 
@@ -568,7 +626,7 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
     hd.pend_depth = 0u;
     while (hd.sims_done < cfg.sims && hd.err == 0u) {
         hd.root_visits += 1u;
-        const BkLeaf lf = bk_tree_select(tr, hd, cfg, root, lane, sm);
+        const BkLeaf lf = bk_tree_select<false>(tr, hd, cfg, root, lane, sm);
         if (!lf.ok) break;
         bk_load(&tr.nodes[lf.parent], lane, L);
         if (!bk_apply(L, lf.tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }
@@ -635,6 +693,147 @@ __device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __res
     }
 }
 
+
+// ---- throughput modes (opt-in, NOT visit-count comparable with the reference) ----
+//
+// (1) Forced plies: a root position with exactly one legal tile has one possible policy record,
+//     [(tile, 1.0)], and one possible action, whatever the simulations do (simulation.rs:213-229); with
+//     BK_MODE_SKIP_FORCED the 800 simulations are not run and the record is written directly.  The returned
+//     training tuple is IDENTICAL to the exact mode's (tests/test_emu_mcts.py, tests/test_gpu_mcts.py).
+// (2) Multi-leaf rounds with virtual loss: up to leaves_per_round simulations of a game are in flight at once,
+//     so one evaluator round serves n_games * leaves_per_round positions (a small batch of games can fill the
+//     tensor cores).  Selections of one round see each other's visits as losses (bk_tree_select<true>).  A
+//     selection that arrives at a leaf already waiting for the evaluator is rolled back and ends the round's
+//     collection.  Invariants kept: every simulation is one evaluated (or terminal) leaf; sum of the root's
+//     child visits == sims_per_move; with one leaf per round the results equal the exact mode bit for bit.
+
+// backup of the multi-leaf mode: the visits were given by the select; add the value, refresh Q
+__device__ __forceinline__ void bk_tree_backup_vl(const BkTree& tr, int depth, const float (&val)[4], int lane,
+                                                  const BkWarpSmem& sm) {
+    for (int d = lane; d < depth; d += 32) {
+        const uint32_t e = sm.path[d];
+        const int tp = int(sm.path_tp[d]);
+        const uint32_t nv = tr.S[e].x;
+        const float w = __fadd_rn(__uint_as_float(tr.X[e].x), bk_sel4f(tp, val[0], val[1], val[2], val[3]));
+        tr.X[e].x = __float_as_uint(w);
+        tr.S[e].y = __float_as_uint(__fdiv_rn(w, float(nv)));
+    }
+    __syncwarp();
+}
+
+// take back the visits a rolled-back selection gave to the interior entries of its path
+__device__ __forceinline__ void bk_tree_unvisit(const BkTree& tr, int depth, int lane, const BkWarpSmem& sm) {
+    for (int d = lane; d < depth; d += 32) {
+        const uint32_t e = sm.path[d];
+        const uint32_t nv = tr.S[e].x - 1u;
+        const float q = nv ? __fdiv_rn(__uint_as_float(tr.X[e].x), float(nv)) : 0.0f;
+        *reinterpret_cast<uint2*>(&tr.S[e]) = make_uint2(nv, __float_as_uint(q));
+    }
+    __syncwarp();
+}
+
+// multi-leaf counterpart of kb_sp_step: policy/value hold leaves_per_round slots per game
+__device__ __forceinline__ void kb_sp_step_vl(const BkSearchCfg& cfg, const BkTree& tr, BkSearchHdr* hdr_g, BkPend* pend_g,
+                                              const float* __restrict__ policy, const float* __restrict__ value,
+                                              unsigned long long* counters, int g, int lane, const BkTabs& tabs,
+                                              BkWarpSmem& sm) {
+    BkSearchHdr hd;
+    hd.n_nodes = hdr_g->n_nodes; hd.n_entries = hdr_g->n_entries; hd.root_visits = hdr_g->root_visits;
+    hd.sims_done = hdr_g->sims_done; hd.pend_kind = hdr_g->pend_kind; hd.pend_count = hdr_g->pend_count;
+    hd.err = hdr_g->err; hd.pol_count = hdr_g->pol_count; hd.plies_searched = hdr_g->plies_searched;
+    hd.forced_plies = hdr_g->forced_plies;
+    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF) return;
+    BkCounters gctr = {0u, 0u};
+    BkSpCounters ctr = {0u, 0u, 0u, 0u};
+    const uint32_t game_id = cfg.first_game_id + uint32_t(g);
+    const uint32_t K = cfg.leaves_per_round;
+    const float* pol = policy + size_t(g) * K * 400;
+    const float* vals = value + size_t(g) * K * 4;
+    BkRegs L;
+    BkBlock root;
+    if (hd.pend_kind == BK_PEND_ROOT) {
+        bk_load(&tr.nodes[0], lane, L);
+        const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, root, 0u, false);   // evaluate(root)
+        hd.n_nodes = 1u;
+        if (id == BK_NODE_NONE) hd.err |= BK_SP_ERR_NO_CHILD;
+        else bk_tree_noise(tr, cfg, game_id, L.ply, lane);
+    } else {
+        root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
+        for (uint32_t j = 0; j < hd.pend_count && hd.err == 0u; ++j) {       // answers are consumed in selection order
+            const BkPend* P = &pend_g[j];
+            const uint32_t slot = P->slot, entry = P->entry;
+            const int depth = int(P->depth);
+            bk_load(&tr.nodes[slot], lane, L);
+            BkBlock blk;
+            const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol + size_t(j) * 400, lane, sm, ctr, blk, slot, false);
+            const int cur = bk_cur(L);
+            bk_tree_link(tr, entry, int(P->tile), id, cur, blk, lane);      // rewrites TN: the pending mark goes
+            float val[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) val[i] = vals[size_t(j) * 4 + ((i + 4 - cur) & 3)];   // value.rotate_right(cur)
+            for (int d = lane; d < depth; d += 32) { sm.path[d] = P->path[d]; sm.path_tp[d] = P->path_tp[d]; }
+            __syncwarp();
+            if (lane == 0) sm.path_tp[depth - 1] = uint8_t(cur);
+            __syncwarp();
+            bk_tree_backup_vl(tr, depth, val, lane, sm);
+            hd.sims_done += 1u;
+            if (lane == 0) ctr.sims += 1u;
+        }
+    }
+    hd.pend_count = 0u;
+    while (hd.sims_done + hd.pend_count < cfg.sims && hd.pend_count < K && hd.err == 0u) {
+        hd.root_visits += 1u;
+        const BkLeaf lf = bk_tree_select<true>(tr, hd, cfg, root, lane, sm);
+        if (!lf.ok) break;
+        if (lf.collide) {                                  // leaf already outstanding: roll back, close the round
+            bk_tree_unvisit(tr, lf.depth - 1, lane, sm);
+            hd.root_visits -= 1u;
+            break;
+        }
+        bk_load(&tr.nodes[lf.parent], lane, L);
+        if (!bk_apply(L, lf.tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }
+        if (lane == 0) ctr.applies += 1u;
+        if (bk_terminal(L)) {
+            float val[4];
+            bk_payoff(L, val);
+            if (lane == 0) sm.path_tp[lf.depth - 1] = 0;
+            __syncwarp();
+            bk_tree_backup_vl(tr, lf.depth, val, lane, sm);
+            hd.sims_done += 1u;
+            if (lane == 0) ctr.sims += 1u;
+            continue;
+        }
+        if (hd.n_nodes >= cfg.max_nodes) { hd.err |= BK_SP_ERR_ENTRY_CAP; break; }
+        const uint32_t slot = hd.n_nodes;
+        hd.n_nodes += 1u;                                   // reserved; stays unused if the leaf gets no child
+        bk_store(&tr.nodes[slot], lane, L);
+        BkPend* P = &pend_g[hd.pend_count];
+        for (int d = lane; d < lf.depth; d += 32) { P->path[d] = sm.path[d]; P->path_tp[d] = sm.path_tp[d]; }
+        if (lane == 0) {
+            P->depth = uint32_t(lf.depth); P->parent = lf.parent; P->tile = uint32_t(lf.tile); P->entry = lf.entry;
+            P->slot = slot;
+            tr.S[lf.entry].w |= 1u << 21;                   // BK_TN_PENDING
+        }
+        __syncwarp();
+        hd.pend_count += 1u;
+    }
+    hd.pend_kind = hd.pend_count ? BK_PEND_LEAF : BK_PEND_DONE;
+    if (lane == 0) {
+        hdr_g->n_nodes = hd.n_nodes; hdr_g->n_entries = hd.n_entries; hdr_g->root_visits = hd.root_visits;
+        hdr_g->sims_done = hd.sims_done; hdr_g->pend_kind = hd.pend_kind; hdr_g->pend_count = hd.pend_count;
+        hdr_g->pend_depth = 0u; hdr_g->err = hd.err; hdr_g->pol_count = hd.pol_count;
+        hdr_g->plies_searched = hd.plies_searched; hdr_g->forced_plies = hd.forced_plies;
+    }
+    const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
+    if (lane == 0 && counters) {
+        atomicAdd(&counters[0], (unsigned long long)ctr.sims);
+        atomicAdd(&counters[1], (unsigned long long)ctr.applies);
+        atomicAdd(&counters[2], (unsigned long long)gctr.movegens);
+        atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
+        atomicAdd(&counters[4], (unsigned long long)ctr.entries);
+        atomicAdd(&counters[5], (unsigned long long)ctr.nodes);
+    }
+}
 
 // ---- training tensors (the consumer side, model/training.py:70-119 `save()`), built on the device -------------
 // For ply i of a game with mover p: planes 0..3 = squares laid BEFORE ply i by seats p, p+1, p+2, p+3; plane 4 =

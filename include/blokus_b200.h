@@ -205,6 +205,22 @@ int bk_selfplay_begin_ply(bk_selfplay* sp);
 int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending_out);
 int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* pending_out);
 int bk_selfplay_end_ply(bk_selfplay* sp);
+/* Opt-in throughput modes.  The default (flags 0, leaves_per_round 1) is the
+ * reference's exact behaviour — mcts() runs sims_per_move simulations one at a time from a fresh tree
+ * (simulation.rs:183,192-210) — and is the only mode whose visit counts are comparable with the reference.
+ *   BK_MODE_SKIP_FORCED      : a root position with exactly ONE legal tile is not searched; its policy record
+ *                              [(tile, sims_per_move visits)] = [(tile, 1.0)] and its action are what the search
+ *                              would return anyway (simulation.rs:213-229), so the training tuple is unchanged.
+ *   leaves_per_round K > 1   : (external-evaluator protocol) up to K simulations per game are in flight per
+ *                              round, separated by virtual loss; leaf_planes / expand_backup then work on
+ *                              [n_games][K] slots: planes [n*K][5][20][20], policy [n*K][400], value [n*K][4]
+ *                              (slot j of game g at index g*K + j; unused slots are zero planes and ignored).
+ *                              With K == 1 results equal the exact mode bit for bit (BK_MODE_FORCE_MULTI_LEAF
+ *                              runs that code path with K == 1, for tests).
+ * Must be called between plies (BK_ERR_STATE otherwise).  bk_selfplay_run_stub honours BK_MODE_SKIP_FORCED only. */
+#define BK_MODE_SKIP_FORCED 1u
+#define BK_MODE_FORCE_MULTI_LEAF 2u
+int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round);
 /* Run every kernel of this handle (and of its bk_env) on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL = the legacy default stream) so an evaluator enqueued on that stream needs no extra sync. */
 int bk_selfplay_set_stream(bk_selfplay* sp, void* cuda_stream);

@@ -388,3 +388,86 @@ def check_arena(lib, orc, n_games=2, seed=5):
     assert s == scores[0]
     assert qm.requests > 0 and qb.requests > 0 and qm.requests + qb.requests == len(hists[0])
     return scores
+
+
+def _records_equal(a, b):
+    ra, rb = a.policy_records(), b.policy_records()
+    assert len(ra) == len(rb)
+    for ga, gb in zip(ra, rb):
+        assert len(ga) == len(gb)
+        for (t1, v1), (t2, v2) in zip(ga, gb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+
+
+def check_throughput_modes(lib, n_games, cfg_kwargs, max_plies, xp, leaves=4, net_seed=0):
+    """SURVEY §8f row f3 — the opt-in throughput modes have no reference counterpart, so they are checked
+    against the exact mode and through invariants:
+      * multi-leaf code path with ONE leaf per round == exact mode, bit for bit;
+      * SKIP_FORCED leaves the training tuple unchanged (external protocol and fused stub kernel);
+      * K leaves per round: every ply's root visits sum to sims_per_move, fewer evaluator rounds, game valid."""
+    from blokus_self_play import SelfPlay, Config, host_evaluator, MODE_SKIP_FORCED, MODE_FORCE_MULTI_LEAF
+    batched, _ = fixed_network(net_seed)
+    ev = batched if xp == "numpy" else host_evaluator(batched)
+    cfg = Config(**cfg_kwargs)
+
+    exact = SelfPlay(n_games, cfg, lib=lib)
+    info_exact = exact.run_evaluator(ev, max_plies=max_plies, xp=xp)
+
+    one = SelfPlay(n_games, cfg, lib=lib)
+    one.set_mode(MODE_FORCE_MULTI_LEAF, 1)
+    one.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    assert one.env.history() == exact.env.history()
+    _records_equal(one, exact)
+    for x, y in zip(one.last_root(), exact.last_root()):
+        assert np.array_equal(x["value_sum"], y["value_sum"]) and np.array_equal(x["prior"], y["prior"])
+    assert one.counters() == exact.counters()
+    one.close()
+
+    skip = SelfPlay(n_games, cfg, lib=lib)
+    skip.set_mode(MODE_SKIP_FORCED, 1)
+    info_skip = skip.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    assert skip.env.history() == exact.env.history()
+    _records_equal(skip, exact)
+    assert skip.counters()["sims"] <= exact.counters()["sims"]
+    skip.close()
+
+    multi = SelfPlay(n_games, cfg, lib=lib)
+    multi.set_mode(0, leaves)
+    info_multi = multi.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    recs = multi.policy_records()
+    hist = multi.env.history()
+    for g in range(n_games):
+        assert len(recs[g]) == info_multi["plies"] or multi.env.is_terminal()[g]
+        for k, (tiles, visits) in enumerate(recs[g]):
+            assert int(visits.sum()) == cfg.sims_per_move, (g, k, visits)
+            assert np.all(np.diff(tiles) > 0)
+            assert hist[g][k][1] in tiles.tolist()
+    assert multi.counters()["sims"] == sum(len(r) for r in recs) * cfg.sims_per_move
+    assert info_multi["rounds"] < info_exact["rounds"]
+    # determinism of the multi-leaf mode
+    again = SelfPlay(n_games, cfg, lib=lib)
+    again.set_mode(0, leaves)
+    again.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    assert again.env.history() == hist
+    _records_equal(again, multi)
+    again.close()
+    multi.close()
+    exact.close()
+    return {"rounds_exact": info_exact["rounds"], "rounds_multi": info_multi["rounds"], "rounds_skip": info_skip["rounds"]}
+
+
+def check_skip_forced_stub(lib, n_games, cfg_kwargs, max_plies):
+    """Fused stub kernel with SKIP_FORCED: same histories and policy records (as visit vectors: a forced root's
+    single child holds all sims_per_move visits either way), fewer simulations run."""
+    from blokus_self_play import SelfPlay, Config, MODE_SKIP_FORCED
+    cfg = Config(**cfg_kwargs)
+    a = SelfPlay(n_games, cfg, lib=lib)
+    a.run_stub(max_plies)
+    b = SelfPlay(n_games, cfg, lib=lib)
+    b.set_mode(MODE_SKIP_FORCED, 1)
+    b.run_stub(max_plies)
+    assert a.env.history() == b.env.history()
+    _records_equal(a, b)
+    ca, cb = a.counters(), b.counters()
+    a.close(); b.close()
+    return ca["sims"], cb["sims"]

@@ -49,3 +49,18 @@ def test_emu_training_tensors(emu_lib, orc):
 
 def test_emu_arena_play_test_game(emu_lib, orc):
     parity.check_arena(emu_lib, orc, n_games=1, seed=2)
+
+
+def test_emu_throughput_modes(emu_lib, orc):
+    """Row f3: multi-leaf (virtual loss) rounds and the forced-ply shortcut, against the exact mode."""
+    r = parity.check_throughput_modes(emu_lib, 2, dict(sims_per_move=12, sample_moves=2, c_base=19652, c_init=1.25,
+                                                       dirichlet_alpha=0.3, exploration_fraction=0.25, seed=6),
+                                      max_plies=7, xp="numpy", leaves=3)
+    assert r["rounds_multi"] < r["rounds_exact"]
+
+
+def test_emu_skip_forced_stub(emu_lib, orc):
+    full, skipped = parity.check_skip_forced_stub(emu_lib, 1, dict(sims_per_move=8, sample_moves=2, c_base=19652, c_init=1.25,
+                                                                   dirichlet_alpha=0.3, exploration_fraction=0.25, seed=2),
+                                                  max_plies=12)
+    assert skipped < full

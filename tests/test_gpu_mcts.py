@@ -106,3 +106,16 @@ def test_gpu_training_tensors(cuda_lib, orc):
 def test_gpu_arena_play_test_game(cuda_lib, orc):
     """play_test_game / arena on the B200 game engine."""
     parity.check_arena(cuda_lib, orc, n_games=6, seed=5)
+
+
+def test_gpu_throughput_modes(cuda_lib, orc):
+    """Row f3 on the device: multi-leaf path with one leaf == exact mode bit for bit; forced-ply shortcut keeps the
+    training tuple; 8 leaves per round keep the visit-sum invariant and cut the evaluator rounds."""
+    r = parity.check_throughput_modes(cuda_lib, 8, dict(CONFIG3, sims_per_move=96, sample_moves=6, dirichlet_alpha=0.3, seed=8),
+                                      max_plies=14, xp="torch", leaves=8)
+    assert r["rounds_multi"] * 3 < r["rounds_exact"]
+
+
+def test_gpu_skip_forced_stub_full_games(cuda_lib, orc):
+    full, skipped = parity.check_skip_forced_stub(cuda_lib, 8, dict(CONFIG3, sims_per_move=48, seed=4), max_plies=-1)
+    assert skipped < full

@@ -16,6 +16,7 @@ ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--blocks", type=int, default=20)
 ap.add_argument("--width", type=int, default=256)
 ap.add_argument("--fp32", action="store_true")
+ap.add_argument("--leaves", type=int, default=1, help="row f3: leaves per game per evaluator round (virtual loss); 1 = exact mode")
 ap.add_argument("--tc", action="store_true", help="hand-written tcgen05 trunk (bk_conv3x3_bf16) instead of cuDNN")
 a = ap.parse_args()
 torch.manual_seed(20261018)
@@ -29,7 +30,9 @@ else:
 cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03, exploration_fraction=0.25, seed=1)
 sp = SelfPlay(a.games, cfg)
 sp.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-planes = torch.zeros((a.games, 5, 20, 20), dtype=torch.float32, device=dev)
+if a.leaves > 1:
+    sp.set_mode(0, a.leaves)
+planes = torch.zeros((a.games * a.leaves, 5, 20, 20), dtype=torch.float32, device=dev)
 sp.begin_ply()
 sp.leaf_planes(planes.data_ptr(), want_count=False)
 t_eval = t_tree = 0.0
@@ -44,15 +47,19 @@ for r in range(a.warmup + a.rounds):
     sp.leaf_planes(planes.data_ptr(), want_count=False)
     e2.record()
     torch.cuda.synchronize()
+    if r == a.warmup - 1:
+        sims0 = sp.counters()["sims"]
     if r >= a.warmup:
         t_eval += e0.elapsed_time(e1)
         t_tree += e1.elapsed_time(e2)
-        evals += a.games
+        evals += a.games * a.leaves
+sims = sp.counters()["sims"] - sims0     # simulations actually completed (slots left empty by collisions do not count)
 flops_per_leaf = 2 * 400 * (5 * 9 * a.width + 2 * a.blocks * a.width * a.width * 9 + 2 * a.width) + 2 * 400 * 4
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
 tot = (t_eval + t_tree) * 1e-3
 print(json.dumps({
-    "metric": "mcts_leaf_evals_per_sec_resnet", "value": evals / tot, "unit": "sims/s",
+    "metric": "mcts_leaf_evals_per_sec_resnet", "value": sims / tot, "unit": "sims/s",
+    "leaves_per_round": a.leaves, "batch_slots_per_round": a.games * a.leaves, "slot_fill": sims / max(evals, 1),
     "config": f"configs[3]: {a.games} games, 800 sims/move, ResNet({a.blocks},{a.width}) random init, {'hand-written tcgen05 convolutions (bf16 operands, f32 accumulate in TMEM)' if a.tc else ('fp32' if a.fp32 else 'bf16 autocast, channels_last')}, "
               f"eval mode; {a.rounds} lockstep evaluator rounds of the first ply timed",
     "ms_per_round": 1e3 * tot / a.rounds, "ms_eval": t_eval / a.rounds, "ms_tree_kernels": t_tree / a.rounds,
