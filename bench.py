@@ -306,10 +306,9 @@ def main() -> int:
         lane_ops += c["lane_ops"]
         movegens += c["movegens"]
     barrier()
-    clocks = sampler.stop()
 
     # ---- end-to-end timed region (host buffers in and out, every step) -----------------------------
-    for w in range(args.warmup):          # the GPU idled while the clock sampler was read: warm up again
+    for w in range(args.warmup):
         e2e_step(2000 + w)
     barrier()
     t0 = time.perf_counter()
@@ -337,6 +336,7 @@ def main() -> int:
         mcts = mcts_measure(local_rank, rank, args.mcts_plies)
         barrier()
         leaf = leaf_eval_measure(local_rank) if rank == 0 else None
+    clocks = sampler.stop()     # sampled over every timed region: device-resident steps, e2e steps, MCTS, leaf evaluation
 
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
     stats = torch.tensor([region_ms, e2e_s, kernel_ms, mcts["kernel_ms"] if mcts else 0.0], dtype=torch.float64, device="cuda")
