@@ -38,11 +38,17 @@ struct __align__(16) BkState {
     uint32_t t01, t23;    // tiles laid this turn, 16 bits each (at most 4 are ever stored)
     uint32_t ply;         // history length
     uint32_t pad[3];      // [0],[1]: child block offset / count when the record is an MCTS node
-    // Narrowing cache of the turn in progress (derived data; meaningful only while |T| >= 1):
-    uint32_t alive;       // chunks of the candidate table with a surviving placement
+    // Narrowing cache of the turn in progress (derived data; meaningful only while |T| >= 1).  Two forms:
+    //   chunk form   — alive = chunks of the candidate table with a surviving placement; smask[l] bit ch set
+    //                  iff candidate ch*32+l is still consistent with T;
+    //   compact form — (alive bit 31 set) at most 32 survivors, smask[l] = candidate index held by lane l or
+    //                  0xFFFF: later tiles of the turn are then one pass, not one pass per alive chunk.
+    uint32_t alive;
     uint32_t tw[3];       // 9x9-window mask of T round T[0]
-    uint16_t smask[32];   // lane l: bit ch set iff candidate ch*32+l is still consistent with T
+    uint16_t smask[32];
 };
+#define BK_NARROW_COMPACT 0x80000000u
+#define BK_CAND_NONE 0xFFFFu
 static_assert(sizeof(BkState) == 528, "BkState layout");
 
 struct BkRegs {
@@ -56,7 +62,11 @@ struct BkTabs {  // candidate table staged in shared memory
     const uint32_t* w0;
     const uint32_t* w1;
     const uint32_t* w2;
+    uint16_t* scratch;  // 32 entries private to this warp (survivor compaction)
 };
+#ifndef BK_MAX_WARPS_PER_CTA
+#define BK_MAX_WARPS_PER_CTA 4
+#endif
 
 struct BkCounters {  // lane-local partial sums, reduced once per kernel
     uint32_t movegens;  // counted on lane 0 only
@@ -74,7 +84,7 @@ static __constant__ uint8_t c_variant_height[BK_NUM_VARIANTS] = BK_VARIANT_HEIGH
 static __constant__ uint8_t c_variant_ncells[BK_NUM_VARIANTS] = BK_VARIANT_NCELLS_INIT;
 static __constant__ uint16_t c_variant_offsets[BK_NUM_VARIANTS][5] = BK_VARIANT_OFFSETS_INIT;
 
-#define BK_TABS_SMEM_WORDS (3 * BK_NUM_CANDS_PAD)
+#define BK_TABS_SMEM_WORDS (3 * BK_NUM_CANDS_PAD + 16 * BK_MAX_WARPS_PER_CTA)
 
 // All threads of the CTA call this once; the caller must __syncthreads() afterwards.
 __device__ __forceinline__ BkTabs bk_stage_tables(uint32_t* smem) {
@@ -87,6 +97,7 @@ __device__ __forceinline__ BkTabs bk_stage_tables(uint32_t* smem) {
     t.w0 = smem;
     t.w1 = smem + BK_NUM_CANDS_PAD;
     t.w2 = smem + 2 * BK_NUM_CANDS_PAD;
+    t.scratch = reinterpret_cast<uint16_t*>(smem + 3 * BK_NUM_CANDS_PAD) + 32 * (threadIdx.x >> 5);
     return t;
 }
 
@@ -128,6 +139,7 @@ __device__ __forceinline__ void bk_store(BkState* __restrict__ s, int lane, cons
     s->smask[lane] = uint16_t(G.smask);
 }
 
+__device__ __forceinline__ int bk_warp_sum_i(int v) { return int(__reduce_add_sync(BK_FULL, unsigned(v))); }
 __device__ __forceinline__ int bk_cur(const BkRegs& G) { return int(G.meta & 3u); }
 __device__ __forceinline__ uint32_t bk_elim(const BkRegs& G) { return (G.meta >> 2) & 0xFu; }
 __device__ __forceinline__ bool bk_terminal(const BkRegs& G) { return bk_elim(G) == 0xFu; }
@@ -193,6 +205,25 @@ __device__ __forceinline__ uint32_t bk_window_to_row(uint32_t L0, uint32_t L1, u
     return ((slice << tc) >> 4) & BK_ROWMASK;
 }
 
+// Chunk form -> compact form when at most 32 placements survive (deterministic: ascending (lane, chunk) order).
+__device__ __forceinline__ void bk_narrow_compact(BkRegs& G, int lane, const BkTabs& tabs) {
+    const int cnt = __popc(G.smask);
+    const int total = bk_warp_sum_i(cnt);
+    if (total > 32 || total == 0) return;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(BK_FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    int pos = incl - cnt;
+    for (uint32_t m = G.smask; m; m &= m - 1u) tabs.scratch[pos++] = uint16_t((__ffs(m) - 1) * 32 + lane);
+    __syncwarp();
+    G.smask = lane < total ? uint32_t(tabs.scratch[lane]) : BK_CAND_NONE;
+    __syncwarp();
+    G.alive = BK_NARROW_COMPACT;
+}
+
 // First tile t of a turn: S = { turn-start-valid placements containing t }, evaluated inside the 9x9
 // window centred on t (every (variant, cell) candidate contains t by construction).  free_/anch are the
 // TURN-START rows of this lane.  Leaves the survivors in G's narrowing cache.  The 13 chunks are
@@ -241,6 +272,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_first(BkRegs& G, uint32_t free_, u
     out.pid = found - 1;
     out.any_valid = found > 0;
     out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    if ((L0 | L1 | L2) != 0u) bk_narrow_compact(G, lane, tabs);   // the turn goes on: later tiles re-test survivors
     return out;
 }
 
@@ -251,9 +283,31 @@ __device__ __forceinline__ BkNarrow bk_narrow_next(BkRegs& G, int t0, int t, int
     int k; uint32_t b;
     bk_window_bit(t, tr, tc, k, b);
     if (k == 0) G.tw0 |= b; else if (k == 1) G.tw1 |= b; else G.tw2 |= b;
-    const uint32_t* __restrict__ wk = k == 0 ? tabs.w0 : (k == 1 ? tabs.w1 : tabs.w2);
-    uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = G.smask;
+    uint32_t L0 = 0u, L1 = 0u, L2 = 0u;
     int found = 0;
+    if (G.alive & BK_NARROW_COMPACT) {                  // one survivor per lane
+        const uint32_t idx = G.smask;
+        if (idx != BK_CAND_NONE) {
+            const uint32_t w0 = tabs.w0[idx], w1 = tabs.w1[idx], w2 = tabs.w2[idx];
+            if ((k == 0 ? w0 : (k == 1 ? w1 : w2)) & b) {
+                L0 = w0 & 0x7FFFFFFu; L1 = w1; L2 = w2;
+                found = int(w0 >> 27) + 1;
+            } else {
+                G.smask = BK_CAND_NONE;
+            }
+        }
+        L0 = __reduce_or_sync(BK_FULL, L0) & ~G.tw0;
+        L1 = __reduce_or_sync(BK_FULL, L1) & ~G.tw1;
+        L2 = __reduce_or_sync(BK_FULL, L2) & ~G.tw2;
+        found = int(__reduce_max_sync(BK_FULL, unsigned(found)));
+        BkNarrow out;
+        out.pid = found - 1;
+        out.any_valid = found > 0;
+        out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+        return out;
+    }
+    const uint32_t* __restrict__ wk = k == 0 ? tabs.w0 : (k == 1 ? tabs.w1 : tabs.w2);
+    uint32_t smask = G.smask;
     for (uint32_t cm = G.alive; cm; cm &= cm - 1u) {   // warp-uniform
         const int ch = __ffs(cm) - 1;
         const int idx = ch * 32 + lane;
@@ -275,6 +329,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_next(BkRegs& G, int t0, int t, int
     out.pid = found - 1;
     out.any_valid = found > 0;
     out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    if ((L0 | L1 | L2) != 0u) bk_narrow_compact(G, lane, tabs);
     return out;
 }
 
@@ -454,9 +509,12 @@ __device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane
         if (lane >= d) incl += v;
     }
     const int excl = incl - cnt;
-    const bool here = (idx >= excl) && (idx < incl);
-    int tile = 0;
-    if (here) tile = lane * 20 + bk_kth_set_bit(legal, idx - excl);
-    const unsigned who = __ballot_sync(BK_FULL, here);
-    return __shfl_sync(BK_FULL, tile, who ? (__ffs(who) - 1) : 0);
+    const unsigned who = __ballot_sync(BK_FULL, (idx >= excl) && (idx < incl));
+    const int src = who ? (__ffs(who) - 1) : 0;                 // the row that holds the idx-th legal tile
+    const uint32_t row = __shfl_sync(BK_FULL, legal, src);
+    const int k = idx - __shfl_sync(BK_FULL, excl, src);
+    // lane j asks: is column j the k-th set bit of that row?  (all lanes cooperate instead of one lane searching)
+    const bool hit = ((row >> lane) & 1u) && (__popc(row & ((1u << lane) - 1u)) == k);
+    const unsigned col = __ballot_sync(BK_FULL, hit);
+    return src * 20 + (col ? (__ffs(col) - 1) : 0);
 }

@@ -3,9 +3,10 @@ import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "blokus-engine_b200"))
 import numpy as np
-from blokus_self_play import GameBatch
+from blokus_self_play import GameBatch, Lib
+LIB = Lib(os.environ['BK_LIB']) if os.environ.get('BK_LIB') else None
 for n in (4096, 16384, 65536):
-    b = GameBatch(n)
+    b = GameBatch(n, lib=LIB)
     for rep in range(4):
         b.reset()
         t = time.time()
