@@ -9,6 +9,7 @@ whatever advance_player / move generation it triggers.
   value     device-resident throughput: K steps timed with CUDA events on the library's stream, inputs in HBM
   e2e       the same metric through the C-ABI with HOST buffers: H2D of the batch's game ids from pinned
             memory, the kernels, D2H of plies + scores + packed histories into pinned memory, every step
+            (double-buffered over two handles: the copy-out of one batch overlaps the playout of the next)
   roofline  dominant kernel k_playout against the measured HBM peak with SURVEY §8d's 708 B/move, plus the
             integer-issue roofline that actually binds it (int_roofline)
   cpu_baseline  the CPU oracle (C++ restatement of the reference algorithm) on the host cores, bounded sample
@@ -262,28 +263,51 @@ def main() -> int:
         flush.zero_()
         torch.cuda.synchronize()
 
-    # pinned host buffers of the e2e path
-    ids_h = torch.arange(first_id, first_id + n, dtype=torch.int64).to(torch.int32).pin_memory()
-    plies_h = torch.empty(n, dtype=torch.int32).pin_memory()
-    scores_h = torch.empty((n, 4), dtype=torch.int32).pin_memory()
-    hist_h = torch.empty((n, 360), dtype=torch.int16).pin_memory()
-    ids_p, plies_p, scores_p, hist_p = (C.c_void_p(t.data_ptr()) for t in (ids_h, plies_h, scores_h, hist_h))
-    h2d_bytes = ids_h.numel() * 4
-    d2h_bytes = plies_h.numel() * 4 + scores_h.numel() * 4 + hist_h.numel() * 2
+    # pinned host buffers of the e2e path, double-buffered: two handles (each with its own stream), so the
+    # device->host copy of one batch overlaps the playout of the next; every step still moves its ids in and
+    # its results out inside the timed region
+    batch2 = GameBatch(n, device=local_rank)
+    lanes = []
+    for b in (batch, batch2):
+        ids_h = torch.arange(first_id, first_id + n, dtype=torch.int64).to(torch.int32).pin_memory()
+        plies_h = torch.empty(n, dtype=torch.int32).pin_memory()
+        scores_h = torch.empty((n, 4), dtype=torch.int32).pin_memory()
+        hist_h = torch.empty((n, 360), dtype=torch.int16).pin_memory()
+        lanes.append({"b": b, "t": (ids_h, plies_h, scores_h, hist_h),
+                      "p": tuple(C.c_void_p(t.data_ptr()) for t in (ids_h, plies_h, scores_h, hist_h)), "busy": False})
+    h2d_bytes = n * 4
+    d2h_bytes = n * 4 + n * 4 * 4 + n * 360 * 2
 
     def device_step(k: int):
         batch.reset()
         batch.lib.check(batch.lib.bk_env_playout(batch._h, SEED + k, first_id, -1, 0))
 
-    def e2e_step(k: int):
-        batch.reset()
-        batch.run_playout_raw(SEED + k, ids_p)
-        batch.fetch_raw(plies_p, scores_p, hist_p)
+    def e2e_collect(lane) -> int:
+        """wait for the lane's outstanding step and read its result from the pinned host buffers"""
+        if not lane["busy"]:
+            return 0
+        lane["b"].sync()
+        lane["busy"] = False
+        return int(lane["t"][1].sum().item())
+
+    def e2e_step(k: int) -> int:
+        lane = lanes[k & 1]
+        done = e2e_collect(lane)           # step k-2's results (the other lane is still in flight)
+        ids_p, plies_p, scores_p, hist_p = lane["p"]
+        lane["b"].reset()
+        lane["b"].run_playout_raw(SEED + k, ids_p)             # H2D of the ids + the playout, enqueued
+        lane["b"].fetch_raw_async(plies_p, scores_p, hist_p)   # D2H of plies + scores + histories, enqueued
+        lane["busy"] = True
+        return done
+
+    def e2e_drain() -> int:
+        return sum(e2e_collect(l) for l in lanes)
 
     # ---- warm-up -------------------------------------------------------------------------------
     for w in range(args.warmup):
         device_step(1000 + w)
         e2e_step(1000 + w)
+    e2e_drain()
 
     # ---- device-resident timed region ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -310,15 +334,16 @@ def main() -> int:
     # ---- end-to-end timed region (host buffers in and out, every step) -----------------------------
     for w in range(args.warmup):
         e2e_step(2000 + w)
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     e2e_moves = 0
     per_step = []
     for k in range(args.steps):
         ts = time.perf_counter()
-        e2e_step(k)
-        e2e_moves += int(plies_h.sum().item())
+        e2e_moves += e2e_step(k)
         per_step.append(time.perf_counter() - ts)
+    e2e_moves += e2e_drain()            # the last two steps' results land before the clock stops
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if os.environ.get("BK_DEBUG"):
@@ -330,6 +355,7 @@ def main() -> int:
     leaf = None
     if not args.no_mcts:
         batch.close()
+        batch2.close()
         del flush
         torch.cuda.empty_cache()
         barrier()

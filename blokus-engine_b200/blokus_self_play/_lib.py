@@ -86,6 +86,8 @@ _SIGNATURES = {
     "bk_env_playout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32]),
     "bk_env_playout_ids": (C.c_int, [_P, C.c_uint64, _P, C.c_int, C.c_uint32]),
     "bk_env_fetch": (C.c_int, [_P, _P, _P, _P]),
+    "bk_env_fetch_async": (C.c_int, [_P, _P, _P, _P]),
+    "bk_env_sync": (C.c_int, [_P]),
     "bk_probe_int_peak": (C.c_int, [C.c_int, _P, _P]),
     "bk_env_playout_results": (C.c_int, [_P, _P, _P]),
     "bk_env_last_kernel_ms": (C.c_int, [_P, _P]),

@@ -164,6 +164,13 @@ class GameBatch:
         """bk_env_fetch straight into caller-held (pinned) buffers."""
         self.lib.check(self.lib.bk_env_fetch(self._h, plies_ptr, scores_ptr, hist_ptr))
 
+    def fetch_raw_async(self, plies_ptr, scores_ptr, hist_ptr) -> None:
+        """bk_env_fetch_async: enqueue the gather into caller-held pinned buffers; valid after sync()."""
+        self.lib.check(self.lib.bk_env_fetch_async(self._h, plies_ptr, scores_ptr, hist_ptr))
+
+    def sync(self) -> None:
+        self.lib.check(self.lib.bk_env_sync(self._h))
+
     def fetch(self):
         """Finished-batch gather: plies[n], scores[n,4], packed history uint16[n,360] (tile | player<<9)."""
         plies = np.zeros(self.n, dtype=np.int32)

@@ -191,6 +191,8 @@ static int env_cells(bk_env* e, int what, int player, uint8_t* out) {
     return BK_OK;
 }
 
+static int env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out, bool wait);
+
 extern "C" {
 
 const char* bk_last_error(void) { return g_last_error.c_str(); }
@@ -432,6 +434,23 @@ int bk_env_playout_ids(bk_env* e, uint64_t seed, const uint32_t* game_ids, int m
 }
 
 int bk_env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out) {
+    return env_fetch(e, plies_out, scores_out, history_packed_out, true);
+}
+
+int bk_env_fetch_async(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out) {
+    return env_fetch(e, plies_out, scores_out, history_packed_out, false);
+}
+
+int bk_env_sync(bk_env* e) {
+    int rc = env_use(e);
+    if (rc) return rc;
+    BK_CUDA(cudaStreamSynchronize(e->stream));
+    return BK_OK;
+}
+
+}  // extern "C"
+
+static int env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out, bool wait) {
     int rc = env_use(e);
     if (rc) return rc;
     int32_t* d_plies = e->d_i32 + 2 * size_t(e->n);
@@ -444,9 +463,11 @@ int bk_env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_t* h
     if (scores_out) BK_CUDA(cudaMemcpyAsync(scores_out, d_scores, sizeof(int32_t) * 4 * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
     if (history_packed_out)
         BK_CUDA(cudaMemcpyAsync(history_packed_out, e->d_hist, sizeof(uint16_t) * BK_HIST_CAP * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
-    BK_CUDA(cudaStreamSynchronize(e->stream));
+    if (wait) BK_CUDA(cudaStreamSynchronize(e->stream));
     return BK_OK;
 }
+
+extern "C" {
 
 int bk_probe_int_peak(int device, double* lane_ops_per_s_out, float* ms_out) {
     int count = 0;

@@ -2,6 +2,7 @@
 // (include/blokus_b200.h).  Host mirror of self_play/src/lib.rs:9-32 + simulation.rs:267-296, batched.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <cmath>
 #include <vector>
@@ -23,6 +24,8 @@ struct bk_selfplay {
     BkSearchHdr* d_hdr = nullptr;
     BkPend* d_pend = nullptr;         // [n][leaves_per_round], multi-leaf mode only
     bool use_vl = false;
+    int num_sms = 148;
+    int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
     uint32_t* d_pol_off = nullptr;    // [n][BK_HIST_CAP + 1]
     uint16_t* d_pol_tile = nullptr;   // [n][policy_cap]
     uint32_t* d_pol_visits = nullptr; // [n][policy_cap]
@@ -57,7 +60,13 @@ __device__ __forceinline__ BkTree bk_tree_of(const BkPools& pl, const BkSearchCf
     return t;
 }
 
-__global__ void __launch_bounds__(32)
+// MINB = CTAs (= games) the register allocation must let an SM hold.  One simulation is a long dependent
+// chain, so a small batch (<= 12 games per SM) runs fastest with all the registers ptxas wants (166), while a
+// large batch gains more from residency: 126 registers at 16 games/SM, 96 at 20 (measured on B200, 8192 games:
+// 2.55e8 -> 3.84e8 -> 4.31e8 sims/s; 1024 games: 1.79e8 -> 1.69e8 -> 1.47e8; 24 and 32 per SM spill and are slower:
+// profiles/r01_ab_mcts_occupancy.log).  The host picks per batch size.
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB)
 k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies,
                 unsigned long long* counters) {
     __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
@@ -236,6 +245,13 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
     sp->device = device;
     sp->cfg = *cfg;
     sp->first_id = first_game_id;
+#ifndef BK_WARP_EMU
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) sp->num_sms = prop.multiProcessorCount;
+        if (const char* e = getenv("BK_STUB_MIN_BLOCKS")) sp->stub_min_blocks = atoi(e);
+    }
+#endif
     int rc = bk_env_create(n_games, device, &sp->env);
     if (rc) { delete sp; return rc; }
     rc = selfplay_alloc(sp, cfg, first_game_id, max_children_per_game);
@@ -357,8 +373,20 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     if (rc) return rc;
     cudaStream_t st = sp->env->stream;
     BK_CUDA(cudaEventRecord(sp->ev0, st));
-    BK_LAUNCH(k_selfplay_stub, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
-              max_plies, sp->d_counters);
+    const int per_sm = (sp->n + sp->num_sms - 1) / sp->num_sms;     // games an SM would hold if all were resident
+    const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= 9 ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : 20)));
+    if (minb >= 20)
+        BK_LAUNCH(k_selfplay_stub<20>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+                  max_plies, sp->d_counters);
+    else if (minb >= 16)
+        BK_LAUNCH(k_selfplay_stub<16>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+                  max_plies, sp->d_counters);
+    else if (minb >= 12)
+        BK_LAUNCH(k_selfplay_stub<12>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+                  max_plies, sp->d_counters);
+    else
+        BK_LAUNCH(k_selfplay_stub<1>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
+                  max_plies, sp->d_counters);
     BK_CUDA(cudaEventRecord(sp->ev1, st));
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaStreamSynchronize(st));

@@ -141,6 +141,11 @@ int bk_env_playout_ids(bk_env* env, uint64_t seed, const uint32_t* game_ids, int
  * stream (pin them for full PCIe rate): plies_out[g] (history length), scores_out[g][4], and the history
  * packed as uint16 (tile | player << 9), history_packed_out[g][BK_MAX_PLIES].  Pointers may be NULL. */
 int bk_env_fetch(bk_env* env, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out);
+/* The same gather enqueued on the handle's stream WITHOUT waiting (the host buffers should be pinned); the
+ * results are valid after bk_env_sync.  With two handles (each has its own stream) a caller overlaps the
+ * device->host copy of one batch with the playout of the next — the double-buffered end-to-end loop of bench.py. */
+int bk_env_fetch_async(bk_env* env, int32_t* plies_out, int32_t* scores_out, uint16_t* history_packed_out);
+int bk_env_sync(bk_env* env);
 /* Results of the last bk_env_playout: per game steps applied by it, and the chained trace hash
  * (0 unless BK_PLAYOUT_HASH).  Either pointer may be NULL. */
 int bk_env_playout_results(bk_env* env, int32_t* steps_out, uint64_t* hash_out);

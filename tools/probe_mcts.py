@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "blokus-engine_b200"))
 from blokus_self_play import SelfPlay, Config, Lib
 LIB = Lib(os.environ['BK_LIB']) if os.environ.get('BK_LIB') else None
-CASES = [(1024, -1)] if os.environ.get('BK_FULLGAME') else [(1024, 16)] if os.environ.get('BK_QUICK') else [(1024, 4), (1024, 16), (4096, 8), (8192, 8)]
+CASES = [(8192, 12)] if os.environ.get('BK_BIG') else [(1024, -1)] if os.environ.get('BK_FULLGAME') else [(1024, 16)] if os.environ.get('BK_QUICK') else [(1024, 4), (1024, 16), (4096, 8), (8192, 8)]
 cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
              exploration_fraction=0.25, seed=1)
 for n, plies in CASES:
