@@ -139,3 +139,38 @@ def test_gpu_selfplay_with_tcgen05_evaluator(cuda_lib, orc):
     for a, b in zip(ref.last_root(), tc.last_root()):
         assert np.array_equal(a["tile"], b["tile"])
         assert np.allclose(a["prior"], b["prior"], atol=2e-3)
+
+
+def test_serving_wire_format_shapes():
+    """Row f4: request validation of the /process_request body (model/model_server.py:34-36) needs no device."""
+    from blokus_self_play import serving
+    with pytest.raises(ValueError):
+        serving.process_request({"player": 0}, lambda x: x)
+    with pytest.raises(ValueError):
+        serving.process_request({"player": 0, "data": [[[False] * 20] * 20] * 4}, lambda x: x)
+    assert serving.process_requests([], lambda x: x) == []
+
+
+@pytest.mark.gpu
+def test_gpu_serving_matches_reference_server_math(cuda_lib):
+    """POST /process_request of model/model_server.py:38-57 on a position of the B200 engine: the response equals
+    `model(boards.unsqueeze(0))` of the same network (fp32), keys and shapes as the GUI expects."""
+    from blokus_self_play import Game, serving
+    from blokus_self_play.resnet import ResNet, LeafEvaluator
+    torch.manual_seed(5)
+    model = ResNet(2, 16).cuda().eval()
+    g = Game.reset(lib=cuda_lib)
+    for _ in range(7):
+        g.apply(g.get_legal_tiles()[0])
+    req = serving.request_from_game(g)
+    assert set(req) == {"player", "data"} and np.asarray(req["data"]).shape == (5, 20, 20)
+    out = serving.process_request(req, LeafEvaluator(model))
+    assert set(out) == {"policy", "values", "status"} and out["status"] == 200
+    assert len(out["policy"]) == 400 and len(out["values"]) == 4
+    with torch.no_grad():
+        p, v = model(torch.tensor(req["data"], dtype=torch.float32).cuda().unsqueeze(0))
+    assert np.allclose(out["policy"], p[0].cpu().numpy(), atol=1e-6) and np.allclose(out["values"], v[0].cpu().numpy(), atol=1e-6)
+    legal = np.asarray(req["data"])[4].reshape(400)
+    assert np.all(np.asarray(out["policy"])[~legal] == 0) and abs(sum(out["policy"]) - 1.0) < 1e-4
+    many = serving.process_requests([req] * 3, LeafEvaluator(model))
+    assert len(many) == 3 and np.allclose(many[2]["policy"], out["policy"], atol=1e-6)
