@@ -1,5 +1,6 @@
 // blokus_b200.hpp — header-only C++ mirror of the reference's `blokus::game::Game`
-// (blokus/src/game.rs:91-312) over the C ABI of blokus_b200.h.  Value semantics like the Rust type
+// (blokus/src/game.rs:91-312) and of the self_play crate's client (self_play/src/simulation.rs:14-22,267-296,
+// self_play/src/lib.rs:9-32) over the C ABI of blokus_b200.h.  Value semantics like the Rust type
 // (`Game: Clone`): copying a Game clones the device state (bk_env_clone); Err(String) becomes
 // blokus::Error carrying bk_last_error().  A Game is a batch of one; GameBatch exposes n games.
 #pragma once
@@ -122,5 +123,108 @@ public:
 private:
     GameBatch b_;
 };
+
+// ---- self_play crate -------------------------------------------------------------------------------------------
+namespace self_play {
+
+// simulation.rs:14-22 (+ seed: the reference draws from thread_rng and cannot be seeded)
+struct Config {
+    uint32_t sims_per_move = 50, sample_moves = 30;
+    float c_base = 19652.0f, c_init = 1.25f, dirichlet_alpha = 0.3f, exploration_fraction = 0.25f;
+    uint64_t seed = 0;
+    bk_config abi() const {
+        return bk_config{sims_per_move, sample_moves, c_base, c_init, dirichlet_alpha, exploration_fraction, seed};
+    }
+};
+
+// what training_game() returns (simulation.rs:293-295; lib.rs:15)
+struct TrainingGame {
+    std::vector<std::pair<int, int>> history;                 // (player, tile)
+    std::vector<std::vector<std::pair<int, float>>> policies; // per ply: (tile, visits / total visits)
+    std::vector<float> values;                                // payoff, absolute seat order
+};
+
+// n self-play clients on one device; game g has global id first_game_id + g.
+class SelfPlay {
+public:
+    SelfPlay(int n_games, const Config& cfg, uint32_t first_game_id = 0, int device = 0, uint32_t max_children_per_game = 0)
+        : n_(n_games) {
+        const bk_config c = cfg.abi();
+        check(bk_selfplay_create(n_games, device, &c, first_game_id, max_children_per_game, &sp_));
+    }
+    SelfPlay(const SelfPlay&) = delete;
+    SelfPlay& operator=(const SelfPlay&) = delete;
+    ~SelfPlay() { bk_selfplay_destroy(sp_); }
+
+    int size() const { return n_; }
+    bk_selfplay* handle() const { return sp_; }
+    void reset(uint32_t first_game_id) { check(bk_selfplay_reset(sp_, first_game_id)); }
+    // opt-in throughput modes (BK_MODE_SKIP_FORCED, leaves per evaluator round); default = the reference's behaviour
+    void set_mode(uint32_t flags, int leaves_per_round = 1) { check(bk_selfplay_set_mode(sp_, flags, leaves_per_round)); }
+    // training_game() for every client with the fixed-prior stub evaluator, on the device (max_plies < 0: to the end)
+    void run_stub(int max_plies = -1) { check(bk_selfplay_run_stub(sp_, max_plies)); }
+    // training_game() with a caller-supplied evaluator working on DEVICE memory:
+    //   eval(planes[n*K][5][20][20] f32) must fill policy[n*K][400] (mover frame) and value[n*K][4] (relative seats)
+    // — the contract of the reference's inference server (model/training.py:43-67) on one contiguous batch.
+    template <class Eval>
+    void run_evaluator(Eval&& eval, float* dev_planes, float* dev_policy, float* dev_value, int max_plies = -1) {
+        int32_t live = 0;
+        for (int ply = 0; max_plies < 0 || ply < max_plies; ++ply) {
+            check(bk_selfplay_live_games(sp_, &live));
+            if (live == 0) break;
+            check(bk_selfplay_begin_ply(sp_));
+            int32_t pending = 0;
+            check(bk_selfplay_leaf_planes(sp_, dev_planes, &pending));
+            while (pending > 0) {
+                eval(dev_planes, dev_policy, dev_value);
+                check(bk_selfplay_expand_backup(sp_, dev_policy, dev_value, &pending));
+                if (pending > 0) check(bk_selfplay_leaf_planes(sp_, dev_planes, nullptr));
+            }
+            check(bk_selfplay_end_ply(sp_));
+        }
+    }
+    std::vector<TrainingGame> results() const {
+        const size_t n = static_cast<size_t>(n_);
+        const int32_t cap = 32768;
+        std::vector<int32_t> plies(n), off(n * (BK_MAX_PLIES + 1));
+        std::vector<int16_t> tile(n * size_t(cap));
+        std::vector<uint32_t> visits(n * size_t(cap));
+        check(bk_selfplay_results(sp_, plies.data(), off.data(), cap, tile.data(), visits.data()));
+        bk_env* env = bk_selfplay_env(sp_);
+        std::vector<int32_t> cnt(n), pl(n * BK_MAX_PLIES), tl(n * BK_MAX_PLIES);
+        check(bk_env_history(env, cnt.data(), pl.data(), tl.data()));
+        std::vector<float> pay(n * 4);
+        check(bk_env_payoff(env, pay.data()));
+        std::vector<TrainingGame> out(n);
+        for (size_t g = 0; g < n; ++g) {
+            TrainingGame& t = out[g];
+            for (int i = 0; i < cnt[g]; ++i) t.history.emplace_back(pl[g * BK_MAX_PLIES + size_t(i)], tl[g * BK_MAX_PLIES + size_t(i)]);
+            for (int k = 0; k < plies[g]; ++k) {
+                const int32_t a = off[g * (BK_MAX_PLIES + 1) + size_t(k)], b = off[g * (BK_MAX_PLIES + 1) + size_t(k) + 1];
+                uint32_t total = 0;
+                for (int32_t e = a; e < b; ++e) total += visits[g * size_t(cap) + size_t(e)];
+                std::vector<std::pair<int, float>> pol;
+                for (int32_t e = a; e < b; ++e)                                           // simulation.rs:222
+                    pol.emplace_back(int(tile[g * size_t(cap) + size_t(e)]), float(visits[g * size_t(cap) + size_t(e)]) / float(total));
+                t.policies.push_back(std::move(pol));
+            }
+            t.values.assign(pay.begin() + long(g) * 4, pay.begin() + long(g) * 4 + 4);
+        }
+        return out;
+    }
+
+private:
+    int n_ = 0;
+    bk_selfplay* sp_ = nullptr;
+};
+
+// batched play_training_game (lib.rs:9-32) with the stub evaluator: games first_game_id .. first_game_id + n - 1
+inline std::vector<TrainingGame> play_training_games(uint32_t first_game_id, int n_games, const Config& cfg, int device = 0) {
+    SelfPlay sp(n_games, cfg, first_game_id, device);
+    sp.run_stub(-1);
+    return sp.results();
+}
+
+}  // namespace self_play
 
 }  // namespace blokus

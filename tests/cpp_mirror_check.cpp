@@ -26,6 +26,23 @@ int main() {
     try { h.apply(399); ok = false; } catch (const blokus::Error& e) { ok = ok && e.code == BK_ERR_ILLEGAL_MOVE; }
     blokus::Game moved = h.place_piece(0, 0, 0);          // monomino on the start corner; h itself is untouched
     ok = ok && h.history().empty() && moved.history().size() == 1 && moved.current_player() == 1;
+    // self_play crate mirror: two stub self-play games, 24 simulations a move, six plies
+    blokus::self_play::Config cfg;
+    cfg.sims_per_move = 24; cfg.sample_moves = 3; cfg.seed = 5;
+    blokus::self_play::SelfPlay sp(2, cfg, /*first_game_id=*/7);
+    sp.set_mode(BK_MODE_SKIP_FORCED, 1);
+    sp.run_stub(6);
+    const auto games = sp.results();
+    ok = ok && games.size() == 2;
+    for (const auto& tg : games) {
+        ok = ok && tg.history.size() == 6 && tg.policies.size() == 6 && tg.values.size() == 4;
+        for (size_t k = 0; k < tg.policies.size(); ++k) {
+            float sum = 0.0f;
+            bool has_action = false;
+            for (const auto& tp : tg.policies[k]) { sum += tp.second; has_action = has_action || tp.first == tg.history[k].second; }
+            ok = ok && sum > 0.999f && sum < 1.001f && has_action;
+        }
+    }
     std::printf(ok ? "device ok\n" : "FAIL\n");
     return ok ? 0 : 1;
 }
