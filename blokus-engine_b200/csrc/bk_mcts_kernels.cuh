@@ -275,8 +275,17 @@ struct BkLeaf {
 __device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn, uint32_t off) {
 #if !defined(BK_WARP_EMU) && defined(BK_CHILD_PREFETCH)
     if (BK_TN_EXPANDED(tn)) {
+#if BK_CHILD_PREFETCH == 3
+        uint32_t d0, d1;    // real loads whose results are never read: the lines land in L1, nothing waits for them
+        asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d0) : "l"(tr.S + off));
+        asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d1) : "l"(tr.X + off));
+#elif BK_CHILD_PREFETCH == 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tr.S + off));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tr.X + off));
+#else
         asm volatile("prefetch.global.L2 [%0];" ::"l"(tr.S + off));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(tr.X + off));
+#endif
     }
 #else
     (void)tr; (void)tn; (void)off;
@@ -291,15 +300,13 @@ __device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn,
 template <bool VL>
 __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                  const BkBlock& root, int lane, BkWarpSmem& sm) {
-    BkLeaf lf;
-    lf.ok = true;
-    lf.collide = false;
-    lf.parent = 0u; lf.entry = 0u; lf.tile = 0;
     uint32_t node = 0u;
     uint32_t off = root.off;
     int n = int(root.n);
     uint32_t Np = hd.root_visits;
     int depth = 0;
+    uint32_t e = 0u, tn = 0u;
+    bool no_child = false;          // the loop's only exits: this flag, or an unexpanded winner (the leaf)
     for (;;) {
         // If this level's winner turns out to be a leaf, the state of `node` is what the leaf step loads
         // next: ask L2 for its 5 lines now, one level of latency ahead.
@@ -320,7 +327,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
                 b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z;
             }
             const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
-            if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
+            if (kmax == 0u) { no_child = true; break; }
             wi = 31u - uint32_t(__clz(int(__ballot_sync(BK_FULL, key == kmax))));
         } else {
             float best = 0.0f;
@@ -334,16 +341,16 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
             }
             const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
             const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
-            if (kmax == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; break; }
+            if (kmax == 0u) { no_child = true; break; }
             wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
         }
         const int src = int(wi & 31u);                     // child i lives on lane i % 32
-        const uint32_t tn = __shfl_sync(BK_FULL, b_tn, src);
-        if (depth >= BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; break; }
-        const uint32_t e = off + wi;
+        tn = __shfl_sync(BK_FULL, b_tn, src);
+        e = off + wi;
         if (lane == src) {                                 // the winner's lane holds everything the backup needs
-            sm.path[depth] = e; sm.path_n[depth] = b_n; sm.path_w[depth] = b_w;
-            sm.path_tp[depth] = uint8_t(BK_TN_TOPLAY(tn));
+            const int slot = depth & (BK_PATH_CAP - 1);    // a path longer than the cap is reported after the loop
+            sm.path[slot] = e; sm.path_n[slot] = b_n; sm.path_w[slot] = b_w;
+            sm.path_tp[slot] = uint8_t(BK_TN_TOPLAY(tn));
             if (VL && !BK_TN_PENDING(tn)) {
                 const uint32_t nv = b_n + 1u;
                 *reinterpret_cast<uint2*>(&tr.S[e]) =
@@ -351,19 +358,21 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
             }
         }
         ++depth;
-        if (!BK_TN_EXPANDED(tn)) {
-            lf.parent = node;
-            lf.entry = e;
-            lf.tile = int(BK_TN_TILE(tn));
-            lf.collide = VL && BK_TN_PENDING(tn);
-            break;
-        }
+        if (!BK_TN_EXPANDED(tn)) break;                    // the leaf
         Np = __shfl_sync(BK_FULL, b_n, src);
         off = __shfl_sync(BK_FULL, b_off, src);
         node = __shfl_sync(BK_FULL, b_node, src);
         n = int(BK_TN_NCHILD(tn));
     }
+    BkLeaf lf;
+    lf.parent = node;
+    lf.entry = e;
+    lf.tile = int(BK_TN_TILE(tn));
+    lf.collide = VL && !no_child && BK_TN_PENDING(tn);
     lf.depth = depth;
+    lf.ok = true;
+    if (no_child) { hd.err |= BK_SP_ERR_NO_CHILD; lf.ok = false; }
+    if (depth > BK_PATH_CAP) { hd.err |= BK_SP_ERR_PATH_CAP; lf.ok = false; }
     __syncwarp();
     return lf;
 }

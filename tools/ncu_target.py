@@ -23,6 +23,17 @@ elif what == "conv":
         conv3x3(xp, w9, bias, xp, True, 1024, out=out)
     torch.cuda.synchronize()
     print("conv done")
+elif what == "mcts_mid":
+    # mid-game MCTS: 120 plies unprofiled, then 2-ply launches (profile the LAST: ncu -k regex:k_selfplay_stub -s 3 -c 1)
+    cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                 exploration_fraction=0.25, seed=1)
+    sp = SelfPlay(1024, cfg, max_children_per_game=65536)
+    sp.set_mode(1, 1)          # forced-ply shortcut only to reach ply 120 sooner (same games either way)
+    sp.run_stub(60); sp.run_stub(60)
+    sp.set_mode(0, 1)
+    for k in range(2):
+        ms = sp.run_stub(2)
+    print("mcts_mid", sp.counters(), ms)
 else:
     cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
                  exploration_fraction=0.25, seed=1)
