@@ -119,3 +119,25 @@ def test_gpu_throughput_modes(cuda_lib, orc):
 def test_gpu_skip_forced_stub_full_games(cuda_lib, orc):
     full, skipped = parity.check_skip_forced_stub(cuda_lib, 8, dict(CONFIG3, sims_per_move=48, seed=4), max_plies=-1)
     assert skipped < full
+
+
+def test_gpu_config5_shard_width(cuda_lib, orc):
+    """BASELINE.json config 5's per-GPU share at full width: 8192 games x 800 sims (the 20-games-per-SM instantiation of
+    the stub kernel), two plies — visit-sum invariant for every game, and a 48-game batch at global id 3000 (the
+    all-registers instantiation) reproduces that slice: results depend on the global game id only."""
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(**CONFIG3)
+    big = SelfPlay(8192, cfg, first_game_id=0, lib=cuda_lib)
+    big.run_stub(2)
+    recs = big.policy_records()
+    assert all(len(r) == 2 and all(int(v.sum()) == 800 for _, v in r) for r in recs)
+    hist = big.env.history()
+    small = SelfPlay(48, cfg, first_game_id=3000, lib=cuda_lib)
+    small.run_stub(2)
+    assert small.env.history() == hist[3000:3048]
+    for ra, rb in zip(small.policy_records(), recs[3000:3048]):
+        for (t1, v1), (t2, v2) in zip(ra, rb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    c = big.counters()
+    assert c["sims"] == 8192 * 2 * 800
+    big.close(); small.close()
