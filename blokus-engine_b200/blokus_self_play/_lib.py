@@ -28,6 +28,7 @@ PLAYOUT_MAX_TILE = 4
 
 MODE_SKIP_FORCED = 1
 MODE_FORCE_MULTI_LEAF = 2
+MODE_TREE_REUSE = 4
 
 
 class BkError(RuntimeError):

@@ -23,6 +23,7 @@ struct bk_selfplay {
     double* d_scratch = nullptr;
     BkSearchHdr* d_hdr = nullptr;
     BkPend* d_pend = nullptr;         // [n][leaves_per_round], multi-leaf mode only
+    uint32_t* d_remap = nullptr;      // [n][2 * max_nodes], tree-reuse mode only
     bool use_vl = false;
     int num_sms = 148;
     int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
@@ -47,7 +48,7 @@ __global__ void k_sp_summary(const BkState* __restrict__ states, BkSummary* __re
 }
 
 struct BkPools {
-    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr; BkPend* pend;
+    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr; BkPend* pend; uint32_t* remap;
     uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
 };
 
@@ -57,6 +58,7 @@ __device__ __forceinline__ BkTree bk_tree_of(const BkPools& pl, const BkSearchCf
     t.S = pl.S + eo; t.X = pl.X + eo;
     t.nodes = pl.nodes + size_t(g) * cfg.max_nodes;
     t.scratch = pl.scratch + size_t(g) * 400;
+    t.remap = pl.remap ? pl.remap + size_t(g) * 2 * cfg.max_nodes : nullptr;
     return t;
 }
 
@@ -97,6 +99,7 @@ __global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* _
     if (g >= n) return;
     const BkSearchHdr* h = &pl.hdr[g];
     bool pend = h->pend_kind == BK_PEND_ROOT || h->pend_kind == BK_PEND_LEAF;
+    const bool resume = h->pend_kind == BK_PEND_RESUME;   // kept tree: needs a step call but has no position to evaluate
     uint32_t slot = h->n_nodes;                      // exact mode: the tentative node slot
     if (vl) {
         if (h->pend_kind == BK_PEND_ROOT) { pend = j == 0; slot = 0u; }
@@ -111,6 +114,7 @@ __global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* _
         if (threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
     } else {
         for (int e = threadIdx.x; e < 2000; e += blockDim.x) o[e] = 0.0f;
+        if (resume && threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
     }
 }
 
@@ -118,7 +122,7 @@ __global__ void k_sp_count(BkPools pl, int n, int32_t* __restrict__ counts) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t k = pl.hdr[g].pend_kind;
-    if (k == BK_PEND_ROOT || k == BK_PEND_LEAF) atomicAdd(&counts[0], 1);
+    if (k == BK_PEND_ROOT || k == BK_PEND_LEAF || k == BK_PEND_RESUME) atomicAdd(&counts[0], 1);
     if (k == BK_PEND_DONE) atomicAdd(&counts[1], 1);
 }
 
@@ -202,7 +206,7 @@ static float host_exp_f32(float x) { return float(std::exp(double(x))); }  // sa
 static BkPools pools_of(const bk_selfplay* sp) {
     BkPools p;
     p.S = sp->d_S; p.X = sp->d_X; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
-    p.hdr = sp->d_hdr; p.pend = sp->d_pend; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
+    p.hdr = sp->d_hdr; p.pend = sp->d_pend; p.remap = sp->d_remap; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
     return p;
 }
 
@@ -326,6 +330,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_stage);
     cudaFree(sp->d_ply_off);
     cudaFree(sp->d_pend);
+    cudaFree(sp->d_remap);
     if (sp->ev0) cudaEventDestroy(sp->ev0);
     if (sp->ev1) cudaEventDestroy(sp->ev1);
     bk_env_destroy(sp->env);
@@ -347,7 +352,7 @@ int bk_selfplay_reset(bk_selfplay* sp, uint32_t first_game_id) {
 int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) {
     int rc = sp_use(sp);
     if (rc) return rc;
-    if (flags & ~(BK_MODE_SKIP_FORCED | BK_MODE_FORCE_MULTI_LEAF))
+    if (flags & ~(BK_MODE_SKIP_FORCED | BK_MODE_FORCE_MULTI_LEAF | BK_MODE_TREE_REUSE))
         return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_set_mode: unknown flag");
     if (leaves_per_round < 1 || leaves_per_round > BK_MAX_LEAVES_PER_ROUND)
         return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_set_mode: leaves_per_round must be in 1..32");
@@ -359,8 +364,16 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
     const bool vl = leaves_per_round > 1 || (flags & BK_MODE_FORCE_MULTI_LEAF);
     if (vl && (!sp->d_pend || uint32_t(leaves_per_round) > sp->dcfg.leaves_per_round)) {
         cudaFree(sp->d_pend);
+    cudaFree(sp->d_remap);
         sp->d_pend = nullptr;
         BK_CUDA(cudaMalloc(&sp->d_pend, sizeof(BkPend) * size_t(sp->n) * size_t(leaves_per_round)));
+    }
+    if ((flags & BK_MODE_TREE_REUSE) && !sp->d_remap)
+        BK_CUDA(cudaMalloc(&sp->d_remap, sizeof(uint32_t) * 2 * size_t(sp->dcfg.max_nodes) * size_t(sp->n)));
+    if (!(flags & BK_MODE_TREE_REUSE) && (sp->dcfg.mode & BK_MODE_TREE_REUSE_FLAG)) {   // leaving the mode: drop kept trees
+        for (BkSearchHdr& x : h) x.reused = 0u;
+        BK_CUDA(cudaMemcpyAsync(sp->d_hdr, h.data(), sizeof(BkSearchHdr) * h.size(), cudaMemcpyHostToDevice, sp->env->stream));
+        BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     }
     sp->use_vl = vl;
     sp->dcfg.mode = flags;

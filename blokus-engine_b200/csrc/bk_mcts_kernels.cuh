@@ -34,6 +34,7 @@
 // opt-in throughput modes; 0 = the reference's exact behaviour
 #define BK_MODE_SKIP_FORCED_FLAG 1u   // a root position with exactly one legal tile is not searched
 #define BK_MODE_FORCE_VL_FLAG 2u      // run the multi-leaf code path even with one leaf per round (tests)
+#define BK_MODE_TREE_REUSE_FLAG 4u    // the subtree of the played child becomes the next ply's tree
 #define BK_MAX_LEAVES_PER_ROUND 32
 
 #define BK_SP_ERR_ENTRY_CAP 1u
@@ -59,6 +60,7 @@ struct BkTree {
     uint4* X;         // [entry_cap] {W, child_off, node id, -}
     BkState* nodes;   // [max_nodes]; pad[0] = child offset, pad[1] = child count
     double* scratch;  // [400]
+    uint32_t* remap;  // [2 * max_nodes], tree-reuse mode only: new node id / new child-block offset per old node
 };
 
 // persisted per game between launches
@@ -66,7 +68,7 @@ struct BkSearchHdr {
     uint32_t n_nodes, n_entries, root_visits, sims_done;
     uint32_t pend_kind, pend_depth, pend_parent, pend_tile;  // 0 none, 1 root, 2 leaf awaiting evaluator
     uint32_t err, pol_count, plies_searched, pend_entry;
-    uint32_t pend_count, forced_plies, rsv0, rsv1;   // multi-leaf mode: leaves outstanding; plies skipped as forced
+    uint32_t pend_count, forced_plies, reused, rsv1;  // multi-leaf: leaves outstanding; plies skipped as forced; tree kept
     uint32_t path[BK_PATH_CAP];
     uint8_t path_tp[BK_PATH_CAP];
 };
@@ -397,7 +399,7 @@ __device__ __forceinline__ void bk_tree_backup(const BkTree& tr, int depth, cons
 // distribution, then pick the tile to play.
 __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                   uint32_t game_id, uint32_t ply, uint32_t* pol_off, uint16_t* pol_tile,
-                                                  uint32_t* pol_visits, int lane) {
+                                                  uint32_t* pol_visits, int lane, uint32_t* picked_entry = nullptr) {
     const uint32_t off = tr.nodes[0].pad[0];
     const int n = int(tr.nodes[0].pad[1]);
     const uint32_t k = hd.plies_searched;
@@ -438,6 +440,7 @@ __device__ __forceinline__ int bk_tree_finish_ply(const BkTree& tr, BkSearchHdr&
         const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
         pick = int(__reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u)) - 1;
     }
+    if (picked_entry) *picked_entry = off + uint32_t(pick);
     return int(BK_TN_TILE(tr.S[off + uint32_t(pick)].w));
 }
 
@@ -458,6 +461,102 @@ __device__ __forceinline__ bool bk_forced_root(const BkTree& tr, BkSearchHdr& hd
     hd.forced_plies += 1u;
     __syncwarp();
     return true;
+}
+
+// ---- tree reuse (opt-in: BK_MODE_TREE_REUSE) ---------------------------------------
+// After the action is played, the subtree below the chosen root child is compacted IN PLACE to the front of
+// the game's pools and becomes the next ply's tree; the next search then only tops the root up to
+// sims_per_move visits.  (The reference builds a new tree every ply, simulation.rs:183 — visit counts differ.)
+// Node ids and child blocks are allocated in expansion order and a child is always expanded after its parent,
+// so walking the old ids upwards (a) sees a node's membership decided before the node itself and (b) copies
+// every record to an index <= its old one: a forward copy never overwrites what is still to be read.
+// Returns false (fresh tree next ply) when the played child was never expanded.
+__device__ __forceinline__ bool bk_tree_reroot(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
+                                               uint32_t played_entry, int lane) {
+    const uint4 sa = tr.S[played_entry];
+    if (!BK_TN_EXPANDED(sa.w)) return false;
+    const uint32_t r = tr.X[played_entry].z;
+    const uint32_t nn = hd.n_nodes;
+    uint32_t* newid = tr.remap;                      // 0 = not in the subtree, else new id + 1
+    uint32_t* newoff = tr.remap + cfg.max_nodes;
+    for (uint32_t i = lane; i < nn; i += 32) newid[i] = 0u;
+    __syncwarp();
+    if (lane == 0) newid[r] = 1u;
+    __syncwarp();
+    // pass 1: membership, top-down in ascending id order
+    for (uint32_t id = r; id < nn; ++id) {
+        if (newid[id] == 0u) continue;                                   // warp-uniform (same address on every lane)
+        const uint32_t off = tr.nodes[id].pad[0], n = tr.nodes[id].pad[1];
+        for (uint32_t i = lane; i < n; i += 32)
+            if (BK_TN_EXPANDED(tr.S[off + i].w)) newid[tr.X[off + i].z] = 1u;
+        __syncwarp();
+    }
+    // pass 2: new ids / new child-block offsets = ranks by old id (chunked warp scans)
+    uint32_t base_id = 0u, base_off = 0u;
+    for (uint32_t c = r; c < nn; c += 32) {
+        const uint32_t id = c + uint32_t(lane);
+        const uint32_t m = (id < nn && newid[id]) ? 1u : 0u;
+        const uint32_t cnt = m ? tr.nodes[id].pad[1] : 0u;
+        uint32_t im = m, ic = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t vm = __shfl_up_sync(BK_FULL, im, d), vc = __shfl_up_sync(BK_FULL, ic, d);
+            if (lane >= d) { im += vm; ic += vc; }
+        }
+        if (m) { newid[id] = base_id + (im - m) + 1u; newoff[id] = base_off + (ic - cnt); }
+        base_id += __shfl_sync(BK_FULL, im, 31);
+        base_off += __shfl_sync(BK_FULL, ic, 31);
+    }
+    __syncwarp();
+    // pass 3: forward copy with pointer rewrite
+    for (uint32_t id = r; id < nn; ++id) {
+        const uint32_t ni1 = newid[id];
+        if (ni1 == 0u) continue;
+        const uint32_t ni = ni1 - 1u, noff = newoff[id];
+        const uint32_t off = tr.nodes[id].pad[0], n = tr.nodes[id].pad[1];
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + uint32_t(lane);
+            uint4 sv = make_uint4(0u, 0u, 0u, 0u), xv = sv;
+            if (i < n) {
+                sv = tr.S[off + i]; xv = tr.X[off + i];
+                if (BK_TN_EXPANDED(sv.w)) { const uint32_t c = xv.z; xv.y = newoff[c]; xv.z = newid[c] - 1u; }
+            }
+            __syncwarp();                                                 // every lane has read before any lane writes
+            if (i < n) { tr.S[noff + i] = sv; tr.X[noff + i] = xv; }
+            __syncwarp();
+        }
+        if (ni != id) {
+            BkRegs T;
+            bk_load(&tr.nodes[id], lane, T);
+            __syncwarp();
+            bk_store(&tr.nodes[ni], lane, T);
+        }
+        if (lane == 0) { tr.nodes[ni].pad[0] = noff; tr.nodes[ni].pad[1] = n; }
+        __syncwarp();
+    }
+    hd.n_nodes = base_id;
+    hd.n_entries = base_off;
+    hd.reused = 1u;
+    return true;
+}
+
+// start of a ply on a kept tree: the root's visits so far are its children's (each pass through the node chose one)
+__device__ __forceinline__ BkBlock bk_tree_resume(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg, int lane) {
+    BkBlock root;
+    root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
+    uint32_t tot = 0u;
+    for (uint32_t i = lane; i < root.n; i += 32) tot += tr.S[root.off + i].x;
+    tot = __reduce_add_sync(BK_FULL, tot);
+    if (tot > cfg.sims) tot = cfg.sims;                  // (cannot exceed: the child had at most sims visits)
+    hd.root_visits = tot;
+    hd.sims_done = tot;
+    if ((cfg.mode & BK_MODE_SKIP_FORCED_FLAG) && root.n == 1u) {     // forced ply on a kept tree: all visits to the one child
+        if (lane == 0) tr.S[root.off].x = cfg.sims;
+        hd.root_visits = cfg.sims; hd.sims_done = cfg.sims;
+        hd.forced_plies += 1u;
+        __syncwarp();
+    }
+    return root;
 }
 
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
@@ -507,21 +606,32 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
     int plies = 0;
+    hd.reused = hdr_g->reused;
+    hd.n_nodes = hdr_g->n_nodes; hd.n_entries = hdr_g->n_entries;            // (meaningful only with a kept tree)
     while (!bk_terminal(G) && (max_plies < 0 || plies < max_plies) && hd.err == 0u) {
-        hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
-        if (!bk_forced_root(tr, hd, cfg, G, lane)) {                                   // (opt-in shortcut, off by default)
-            BkBlock root;
-            bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);              // evaluate(root), :184
+        BkBlock root;
+        bool search = true;
+        if (hd.reused) {                                                               // (opt-in tree reuse)
+            root = bk_tree_resume(tr, hd, cfg, lane);
+        } else {
+            hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
+            search = !bk_forced_root(tr, hd, cfg, G, lane);                            // (opt-in shortcut, off by default)
+            if (search) bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);  // evaluate(root), :184
+        }
+        if (search) {
             bk_tree_noise(tr, cfg, game_id, G.ply, lane);                              // :190
-            for (uint32_t s = 0; s < cfg.sims && hd.err == 0u; ++s) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
+            while (hd.sims_done < cfg.sims && hd.err == 0u) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
         }
         if (hd.err) break;
-        const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
+        uint32_t played = 0u;
+        const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane, &played);
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;
         if (!bk_apply(G, action, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }   // :288
         if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
         ++plies;
+        hd.reused = 0u;
+        if ((cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G)) bk_tree_reroot(tr, hd, cfg, played, lane);
     }
     bk_store(&states[g], lane, G);
     if (lane == 0) {
@@ -533,6 +643,7 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         hdr_g->root_visits = hd.root_visits;
         hdr_g->sims_done = hd.sims_done;
         hdr_g->forced_plies = hd.forced_plies;
+        hdr_g->reused = hd.reused;
         hdr_g->pend_kind = 0u;
     }
     const unsigned crem = __reduce_add_sync(BK_FULL, gctr.crem);
@@ -552,12 +663,14 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
 #define BK_PEND_ROOT 1u   // root position waiting for the evaluator          (simulation.rs:183-189)
 #define BK_PEND_LEAF 2u   // a leaf position waiting for the evaluator         (simulation.rs:206)
 #define BK_PEND_DONE 3u   // all simulations of this ply are done; waiting for bk_selfplay_end_ply
+#define BK_PEND_RESUME 4u // tree-reuse mode: the root is already expanded; the next step call runs on (no answer to consume)
 
 __device__ __forceinline__ void bk_hdr_load(const BkSearchHdr* h, BkSearchHdr& hd, const BkTree& tr, int lane,
                                             BkWarpSmem& sm) {
     hd.n_nodes = h->n_nodes; hd.n_entries = h->n_entries; hd.root_visits = h->root_visits; hd.sims_done = h->sims_done;
     hd.pend_kind = h->pend_kind; hd.pend_depth = h->pend_depth; hd.pend_parent = h->pend_parent; hd.pend_tile = h->pend_tile;
     hd.err = h->err; hd.pol_count = h->pol_count; hd.plies_searched = h->plies_searched; hd.pend_entry = h->pend_entry;
+    hd.pend_count = h->pend_count; hd.forced_plies = h->forced_plies; hd.reused = h->reused;
     for (int d = lane; d < int(hd.pend_depth) && d < BK_PATH_CAP; d += 32) {
         const uint32_t e = h->path[d];
         sm.path[d] = e; sm.path_tp[d] = h->path_tp[d];
@@ -573,6 +686,7 @@ __device__ __forceinline__ void bk_hdr_store(BkSearchHdr* h, const BkSearchHdr& 
         h->n_nodes = hd.n_nodes; h->n_entries = hd.n_entries; h->root_visits = hd.root_visits; h->sims_done = hd.sims_done;
         h->pend_kind = hd.pend_kind; h->pend_depth = hd.pend_depth; h->pend_parent = hd.pend_parent; h->pend_tile = hd.pend_tile;
         h->err = hd.err; h->pol_count = hd.pol_count; h->plies_searched = hd.plies_searched; h->pend_entry = hd.pend_entry;
+        h->pend_count = hd.pend_count; h->forced_plies = hd.forced_plies; h->reused = hd.reused;
     }
 }
 
@@ -583,16 +697,26 @@ __device__ __forceinline__ void kb_sp_begin(const BkSearchCfg& cfg, const BkStat
     bk_load(&states[g], lane, G);
     const bool live = !bk_terminal(G) && hdr_g->err == 0u;
     BkSearchHdr hd;
-    hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;
     hd.forced_plies = hdr_g->forced_plies;
-    const bool forced = live && bk_forced_root(tr, hd, cfg, G, lane);      // opt-in shortcut, off by default
-    if (live && !forced) bk_store(&tr.nodes[0], lane, G);
+    hd.reused = live ? hdr_g->reused : 0u;
+    uint32_t kind = live ? BK_PEND_ROOT : BK_PEND_NONE;
+    if (hd.reused) {                                                       // opt-in tree reuse: the root is expanded already
+        hd.n_nodes = hdr_g->n_nodes; hd.n_entries = hdr_g->n_entries;
+        bk_tree_resume(tr, hd, cfg, lane);
+        bk_tree_noise(tr, cfg, cfg.first_game_id + uint32_t(g), G.ply, lane);
+        kind = hd.sims_done >= cfg.sims ? BK_PEND_DONE : BK_PEND_RESUME;
+    } else {
+        hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;
+        const bool forced = live && bk_forced_root(tr, hd, cfg, G, lane);  // opt-in shortcut, off by default
+        if (live && !forced) bk_store(&tr.nodes[0], lane, G);
+        if (forced) kind = BK_PEND_DONE;
+    }
     if (lane == 0) {
         hdr_g->n_nodes = hd.n_nodes; hdr_g->n_entries = hd.n_entries; hdr_g->root_visits = hd.root_visits;
-        hdr_g->sims_done = hd.sims_done; hdr_g->forced_plies = hd.forced_plies;
+        hdr_g->sims_done = hd.sims_done; hdr_g->forced_plies = hd.forced_plies; hdr_g->reused = hd.reused;
         hdr_g->pend_depth = 0u; hdr_g->pend_parent = 0u; hdr_g->pend_tile = 0u; hdr_g->pend_entry = 0u;
         hdr_g->pend_count = 0u;
-        hdr_g->pend_kind = !live ? BK_PEND_NONE : (forced ? BK_PEND_DONE : BK_PEND_ROOT);
+        hdr_g->pend_kind = kind;
     }
 }
 
@@ -604,19 +728,22 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
                                            BkWarpSmem& sm) {
     BkSearchHdr hd;
     bk_hdr_load(hdr_g, hd, tr, lane, sm);
-    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF) return;
+    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF && hd.pend_kind != BK_PEND_RESUME) return;
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
     const float* pol = policy + size_t(g) * 400;
     BkRegs L;
-    bk_load(&tr.nodes[hd.n_nodes], lane, L);            // the pending position (tentative node slot)
     BkBlock root;
-    if (hd.pend_kind == BK_PEND_ROOT) {
+    if (hd.pend_kind == BK_PEND_RESUME) {                // kept tree: nothing to consume, run on
+        root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
+    } else if (hd.pend_kind == BK_PEND_ROOT) {
+        bk_load(&tr.nodes[hd.n_nodes], lane, L);        // the pending position (tentative node slot)
         bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, root);                      // evaluate(root), value dropped
         if (hd.n_nodes == 0u) { hd.err |= BK_SP_ERR_NO_CHILD; }                         // reference: unwrap on None
         else bk_tree_noise(tr, cfg, game_id, L.ply, lane);
     } else {
+        bk_load(&tr.nodes[hd.n_nodes], lane, L);
         root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
         BkBlock blk;
         const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, blk);
@@ -683,13 +810,16 @@ __device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __res
     bk_load(&states[g], lane, G);
     BkCounters gctr = {0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
-    const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane);
+    uint32_t played = 0u;
+    const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane, &played);
     const int p = bk_cur(G);
     const uint32_t ply = G.ply;
+    hd.reused = 0u;
     if (!bk_apply(G, action, -1, lane, tabs, gctr)) hd.err |= BK_SP_ERR_APPLY;
     else {
         if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
         bk_store(&states[g], lane, G);
+        if ((cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G)) bk_tree_reroot(tr, hd, cfg, played, lane);
     }
     hd.pend_kind = BK_PEND_NONE;
     hd.pend_depth = 0u;
@@ -751,7 +881,7 @@ __device__ __forceinline__ void kb_sp_step_vl(const BkSearchCfg& cfg, const BkTr
     hd.sims_done = hdr_g->sims_done; hd.pend_kind = hdr_g->pend_kind; hd.pend_count = hdr_g->pend_count;
     hd.err = hdr_g->err; hd.pol_count = hdr_g->pol_count; hd.plies_searched = hdr_g->plies_searched;
     hd.forced_plies = hdr_g->forced_plies;
-    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF) return;
+    if (hd.pend_kind != BK_PEND_ROOT && hd.pend_kind != BK_PEND_LEAF && hd.pend_kind != BK_PEND_RESUME) return;
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
@@ -760,7 +890,9 @@ __device__ __forceinline__ void kb_sp_step_vl(const BkSearchCfg& cfg, const BkTr
     const float* vals = value + size_t(g) * K * 4;
     BkRegs L;
     BkBlock root;
-    if (hd.pend_kind == BK_PEND_ROOT) {
+    if (hd.pend_kind == BK_PEND_RESUME) {                // kept tree: nothing to consume, run on
+        root.off = tr.nodes[0].pad[0]; root.n = tr.nodes[0].pad[1];
+    } else if (hd.pend_kind == BK_PEND_ROOT) {
         bk_load(&tr.nodes[0], lane, L);
         const uint32_t id = bk_tree_expand(tr, hd, cfg, L, pol, lane, sm, ctr, root, 0u, false);   // evaluate(root)
         hd.n_nodes = 1u;

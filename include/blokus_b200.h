@@ -222,9 +222,16 @@ int bk_selfplay_end_ply(bk_selfplay* sp);
  *                              (slot j of game g at index g*K + j; unused slots are zero planes and ignored).
  *                              With K == 1 results equal the exact mode bit for bit (BK_MODE_FORCE_MULTI_LEAF
  *                              runs that code path with K == 1, for tests).
- * Must be called between plies (BK_ERR_STATE otherwise).  bk_selfplay_run_stub honours BK_MODE_SKIP_FORCED only. */
+ *   BK_MODE_TREE_REUSE       : after a ply's action is played, the subtree below the chosen root child is
+ *                              compacted in place and becomes the next ply's tree; that search adds fresh root
+ *                              noise and only tops the root up to sims_per_move visits (the reference starts a
+ *                              new tree every ply, simulation.rs:183).  Every recorded policy still sums to
+ *                              sims_per_move visits.
+ * Must be called between plies (BK_ERR_STATE otherwise).  bk_selfplay_run_stub honours BK_MODE_SKIP_FORCED and
+ * BK_MODE_TREE_REUSE; leaves_per_round applies to the external-evaluator protocol. */
 #define BK_MODE_SKIP_FORCED 1u
 #define BK_MODE_FORCE_MULTI_LEAF 2u
+#define BK_MODE_TREE_REUSE 4u
 int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round);
 /* Run every kernel of this handle (and of its bk_env) on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL = the legacy default stream) so an evaluator enqueued on that stream needs no extra sync. */

@@ -471,3 +471,63 @@ def check_skip_forced_stub(lib, n_games, cfg_kwargs, max_plies):
     ca, cb = a.counters(), b.counters()
     a.close(); b.close()
     return ca["sims"], cb["sims"]
+
+
+def check_tree_reuse(lib, n_games, cfg_kwargs, max_plies, xp, net_seed=0):
+    """Row f3, tree reuse (opt-in; no reference counterpart — the reference starts a new tree every ply):
+      * every recorded policy sums to sims_per_move visits, children ascending, the played tile among them;
+      * fewer simulations are run than in the exact mode (the kept subtree's visits are not repeated);
+      * deterministic; the fused stub kernel and the evaluator protocol driven by the stub's own policy/value agree;
+      * stop-and-resume (max_plies prefixes) equals one run; combined with the forced-ply shortcut and with
+        multi-leaf rounds the invariants still hold."""
+    from blokus_self_play import SelfPlay, Config, host_evaluator, MODE_TREE_REUSE, MODE_SKIP_FORCED
+    cfg = Config(**cfg_kwargs)
+
+    def invariants(sp, plies):
+        recs, hist = sp.policy_records(), sp.env.history()
+        for g in range(n_games):
+            assert len(recs[g]) == min(plies, len(hist[g])) or sp.env.is_terminal()[g]
+            for k, (tiles, visits) in enumerate(recs[g]):
+                assert int(visits.sum()) == cfg.sims_per_move, (g, k, visits)
+                assert np.all(np.diff(tiles) > 0) and hist[g][k][1] in tiles.tolist()
+
+    exact = SelfPlay(n_games, cfg, lib=lib)
+    exact.run_stub(max_plies)
+    sims_exact = exact.counters()["sims"]
+    exact.close()
+
+    a = SelfPlay(n_games, cfg, lib=lib)
+    a.set_mode(MODE_TREE_REUSE, 1)
+    a.run_stub(max_plies)
+    invariants(a, max_plies)
+    assert a.counters()["sims"] < sims_exact
+
+    b = SelfPlay(n_games, cfg, lib=lib)                       # prefixes compose (the kept tree survives between launches)
+    b.set_mode(MODE_TREE_REUSE, 1)
+    b.run_stub(max_plies // 2)
+    b.run_stub(max_plies - max_plies // 2)
+    assert b.env.history() == a.env.history()
+    _records_equal(a, b)
+    b.close()
+
+    def stub_eval(pl):                                        # the stub as an external evaluator
+        pl = np.asarray(pl.detach().cpu().numpy() if hasattr(pl, "detach") else pl)
+        return pl[:, 4].reshape(-1, 400).astype(np.float32).copy(), np.full((pl.shape[0], 4), 0.25, dtype=np.float32)
+    ev = stub_eval if xp == "numpy" else host_evaluator(stub_eval)
+    c = SelfPlay(n_games, cfg, lib=lib)
+    c.set_mode(MODE_TREE_REUSE, 1)
+    c.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    assert c.env.history() == a.env.history()
+    _records_equal(a, c)
+    assert c.counters()["sims"] == a.counters()["sims"]
+    c.close()
+
+    d = SelfPlay(n_games, cfg, lib=lib)                       # with the forced-ply shortcut and 3 leaves per round
+    d.set_mode(MODE_TREE_REUSE | MODE_SKIP_FORCED, 3)
+    batched, _ = fixed_network(net_seed)
+    d.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, xp=xp)
+    invariants(d, max_plies)
+    d.close()
+    sims_reuse = a.counters()["sims"]
+    a.close()
+    return sims_exact, sims_reuse

@@ -64,3 +64,10 @@ def test_emu_skip_forced_stub(emu_lib, orc):
                                                                    dirichlet_alpha=0.3, exploration_fraction=0.25, seed=2),
                                                   max_plies=12)
     assert skipped < full
+
+
+def test_emu_tree_reuse(emu_lib, orc):
+    full, reuse = parity.check_tree_reuse(emu_lib, 2, dict(sims_per_move=20, sample_moves=2, c_base=19652, c_init=1.25,
+                                                          dirichlet_alpha=0.3, exploration_fraction=0.25, seed=12),
+                                          max_plies=8, xp="numpy")
+    assert reuse < full

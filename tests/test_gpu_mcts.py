@@ -141,3 +141,11 @@ def test_gpu_config5_shard_width(cuda_lib, orc):
     c = big.counters()
     assert c["sims"] == 8192 * 2 * 800
     big.close(); small.close()
+
+
+def test_gpu_tree_reuse(cuda_lib, orc):
+    """Row f3, tree reuse on the device (256 sims, 24 plies, 6 games): invariants, determinism across launch
+    splits, fused kernel == evaluator protocol, fewer simulations than the exact mode."""
+    full, reuse = parity.check_tree_reuse(cuda_lib, 6, dict(CONFIG3, sims_per_move=256, sample_moves=6, dirichlet_alpha=0.3, seed=21),
+                                          max_plies=24, xp="torch")
+    assert reuse < full
