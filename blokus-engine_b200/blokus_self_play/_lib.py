@@ -110,6 +110,8 @@ _SIGNATURES = {
     "bk_selfplay_live_games": (C.c_int, [_P, _P]),
     "bk_selfplay_env": (_P, [_P]),
     "bk_selfplay_results": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
+    "bk_selfplay_results_sizes": (C.c_int, [_P, _P, _P, _P, _P]),
+    "bk_selfplay_results_packed": (C.c_int, [_P, _P, _P, _P]),
     "bk_selfplay_last_root": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "bk_selfplay_training_sizes": (C.c_int, [_P, _P, _P]),
     "bk_selfplay_training_tensors": (C.c_int, [_P, _P, _P, _P]),

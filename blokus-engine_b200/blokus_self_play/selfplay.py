@@ -171,6 +171,19 @@ class SelfPlay:
             out.append(recs)
         return out
 
+    def policy_records_packed(self):
+        """All policy records as one compressed-row structure (bk_selfplay_results_packed): (ply_offset int64[n+1],
+        ply_ptr int64[P+1], tiles int16[E], visits uint32[E]); ply k of game g owns entries
+        ply_ptr[ply_offset[g]+k] : ply_ptr[ply_offset[g]+k+1].  One kernel and three copies whatever the batch size."""
+        tp, te = C.c_int64(0), C.c_int64(0)
+        ply_off = np.zeros(self.n + 1, dtype=np.int64)
+        self.lib.check(self.lib.bk_selfplay_results_sizes(self._h, C.byref(tp), C.byref(te), _ptr(ply_off), None))
+        ply_ptr = np.zeros(tp.value + 1, dtype=np.int64)
+        tiles = np.zeros(max(te.value, 1), dtype=np.int16)
+        visits = np.zeros(max(te.value, 1), dtype=np.uint32)
+        self.lib.check(self.lib.bk_selfplay_results_packed(self._h, _ptr(ply_ptr), _ptr(tiles), _ptr(visits)))
+        return ply_off, ply_ptr, tiles[: te.value], visits[: te.value]
+
     def last_root(self):
         """Root children of the last searched ply: per game dict(tile, visits, value_sum, prior)."""
         cnt = np.zeros(self.n, dtype=np.int32)

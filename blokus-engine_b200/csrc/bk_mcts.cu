@@ -35,6 +35,11 @@ struct bk_selfplay {
     unsigned long long* d_counters = nullptr;  // [8], cumulative
     uint8_t* d_stage = nullptr;       // [n][400 * 16] gather staging for last_root
     int64_t* d_ply_off = nullptr;     // [n + 1] prefix of plies per game (training tensors)
+    int64_t* d_pack_off = nullptr;    // [2][n + 1] prefixes of plies / policy entries per game (packed results)
+    int64_t* d_pack_ptr = nullptr;    // [pack_plies + 1]
+    uint16_t* d_pack_tile = nullptr;  // [pack_entries]
+    uint32_t* d_pack_visits = nullptr;
+    int64_t pack_plies = -1, pack_entries = -1, pack_cap_plies = 0, pack_cap_entries = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.0f;
 };
@@ -178,6 +183,23 @@ k_training_tensors(BkSearchCfg cfg, BkPools pl, const uint16_t* hist, const BkSu
                         pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap,
                         int(ply_off[g + 1] - o), summary[g].payoff, states + o * 2000, policies + o * 400, values + o * 4,
                         own, dense, legal, threadIdx.x, blockDim.x);
+}
+
+// pack every game's policy records into one CSR: ply_ptr[ply_off[g] + k] = first entry of ply k of game g in the
+// packed arrays (plus one closing entry at ply_ptr[total_plies]), tiles / visits copied game after game
+__global__ void k_pack_results(BkSearchCfg cfg, BkPools pl, int n, const int64_t* __restrict__ ply_off,
+                               const int64_t* __restrict__ ent_off, int64_t* __restrict__ ply_ptr,
+                               uint16_t* __restrict__ tile, uint32_t* __restrict__ visits) {
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const uint32_t plies = pl.hdr[g].plies_searched, cnt = pl.hdr[g].pol_count;
+    const uint32_t* off = pl.pol_off + size_t(g) * (BK_HIST_CAP + 1);
+    const uint16_t* st = pl.pol_tile + size_t(g) * cfg.policy_cap;
+    const uint32_t* sv = pl.pol_visits + size_t(g) * cfg.policy_cap;
+    const int64_t p0 = ply_off[g], e0 = ent_off[g];
+    for (uint32_t k = threadIdx.x; k < plies; k += blockDim.x) ply_ptr[p0 + k] = e0 + int64_t(off[k]);
+    for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) { tile[e0 + e] = st[e]; visits[e0 + e] = sv[e]; }
+    if (g == n - 1 && threadIdx.x == 0) ply_ptr[ply_off[n]] = ent_off[n];
 }
 
 // gather the root's child block (tile, visits, value_sum, prior) of every game: out[g][400] x 4 arrays
@@ -331,6 +353,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_ply_off);
     cudaFree(sp->d_pend);
     cudaFree(sp->d_remap);
+    cudaFree(sp->d_pack_off); cudaFree(sp->d_pack_ptr); cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits);
     if (sp->ev0) cudaEventDestroy(sp->ev0);
     if (sp->ev1) cudaEventDestroy(sp->ev1);
     bk_env_destroy(sp->env);
@@ -365,6 +388,7 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
     if (vl && (!sp->d_pend || uint32_t(leaves_per_round) > sp->dcfg.leaves_per_round)) {
         cudaFree(sp->d_pend);
     cudaFree(sp->d_remap);
+    cudaFree(sp->d_pack_off); cudaFree(sp->d_pack_ptr); cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits);
         sp->d_pend = nullptr;
         BK_CUDA(cudaMalloc(&sp->d_pend, sizeof(BkPend) * size_t(sp->n) * size_t(leaves_per_round)));
     }
@@ -532,6 +556,63 @@ int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off
                                     sizeof(uint32_t) * h[g].pol_count, cudaMemcpyDeviceToHost, sp->env->stream));
     }
     BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    return BK_OK;
+}
+
+int bk_selfplay_results_sizes(bk_selfplay* sp, int64_t* total_plies_out, int64_t* total_entries_out, int64_t* ply_offset_out,
+                              int64_t* entry_offset_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    const size_t n = size_t(sp->n);
+    cudaStream_t st = sp->env->stream;
+    std::vector<BkSearchHdr> h(n);
+    BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    std::vector<int64_t> off(2 * (n + 1), 0);
+    for (size_t g = 0; g < n; ++g) {
+        off[g + 1] = off[g] + int64_t(h[g].plies_searched);
+        off[n + 1 + g + 1] = off[n + 1 + g] + int64_t(h[g].pol_count);
+    }
+    if (!sp->d_pack_off) BK_CUDA(cudaMalloc(&sp->d_pack_off, sizeof(int64_t) * 2 * (n + 1)));
+    BK_CUDA(cudaMemcpyAsync(sp->d_pack_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    sp->pack_plies = off[n];
+    sp->pack_entries = off[2 * n + 1];
+    if (total_plies_out) *total_plies_out = sp->pack_plies;
+    if (total_entries_out) *total_entries_out = sp->pack_entries;
+    if (ply_offset_out) for (size_t g = 0; g <= n; ++g) ply_offset_out[g] = off[g];
+    if (entry_offset_out) for (size_t g = 0; g <= n; ++g) entry_offset_out[g] = off[n + 1 + g];
+    return BK_OK;
+}
+
+int bk_selfplay_results_packed(bk_selfplay* sp, int64_t* ply_ptr_out, int16_t* tile_out, uint32_t* visits_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (sp->pack_plies < 0) return bk_fail(BK_ERR_STATE, "bk_selfplay_results_packed: call bk_selfplay_results_sizes first");
+    if (!ply_ptr_out || !tile_out || !visits_out) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_results_packed: null output");
+    cudaStream_t st = sp->env->stream;
+    if (sp->pack_plies + 1 > sp->pack_cap_plies) {
+        cudaFree(sp->d_pack_ptr); sp->d_pack_ptr = nullptr; sp->pack_cap_plies = 0;
+        BK_CUDA(cudaMalloc(&sp->d_pack_ptr, sizeof(int64_t) * size_t(sp->pack_plies + 1)));
+        sp->pack_cap_plies = sp->pack_plies + 1;
+    }
+    if (sp->pack_entries + 1 > sp->pack_cap_entries) {
+        cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits); sp->d_pack_tile = nullptr; sp->d_pack_visits = nullptr;
+        sp->pack_cap_entries = 0;
+        BK_CUDA(cudaMalloc(&sp->d_pack_tile, sizeof(uint16_t) * size_t(sp->pack_entries + 1)));
+        BK_CUDA(cudaMalloc(&sp->d_pack_visits, sizeof(uint32_t) * size_t(sp->pack_entries + 1)));
+        sp->pack_cap_entries = sp->pack_entries + 1;
+    }
+    BK_LAUNCH(k_pack_results, sp->n, 256, st, sp->dcfg, pools_of(sp), sp->n, sp->d_pack_off, sp->d_pack_off + (sp->n + 1),
+              sp->d_pack_ptr, sp->d_pack_tile, sp->d_pack_visits);
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaMemcpyAsync(ply_ptr_out, sp->d_pack_ptr, sizeof(int64_t) * size_t(sp->pack_plies + 1), cudaMemcpyDeviceToHost, st));
+    if (sp->pack_entries > 0) {
+        BK_CUDA(cudaMemcpyAsync(tile_out, sp->d_pack_tile, sizeof(uint16_t) * size_t(sp->pack_entries), cudaMemcpyDeviceToHost, st));
+        BK_CUDA(cudaMemcpyAsync(visits_out, sp->d_pack_visits, sizeof(uint32_t) * size_t(sp->pack_entries), cudaMemcpyDeviceToHost, st));
+    }
+    BK_CUDA(cudaStreamSynchronize(st));
+    sp->pack_plies = -1;     // sizes are valid for one gather: the games may move on
     return BK_OK;
 }
 

@@ -248,6 +248,15 @@ bk_env* bk_selfplay_env(bk_selfplay* sp);
  *   too small. */
 int bk_selfplay_results(bk_selfplay* sp, int32_t* plies_out, int32_t* policy_off_out, int32_t policy_cap,
                         int16_t* policy_tile_out, uint32_t* policy_visits_out);
+/* The same records as ONE compressed-row gather for large batches (one kernel, three copies instead of two copies per
+ * game): bk_selfplay_results_sizes returns the totals and the per-game prefixes (n_games + 1 entries each; any pointer
+ * may be NULL) and must be called first; bk_selfplay_results_packed then fills HOST buffers
+ *   ply_ptr_out[total_plies + 1]   entry range of ply k of game g: [ply_ptr[ply_offset[g] + k], ply_ptr[ply_offset[g] + k + 1])
+ *   tile_out[total_entries], visits_out[total_entries]
+ * (pinned buffers give the full PCIe rate). */
+int bk_selfplay_results_sizes(bk_selfplay* sp, int64_t* total_plies_out, int64_t* total_entries_out, int64_t* ply_offset_out,
+                              int64_t* entry_offset_out);
+int bk_selfplay_results_packed(bk_selfplay* sp, int64_t* ply_ptr_out, int16_t* tile_out, uint32_t* visits_out);
 /* Root children of the LAST searched ply of each game (debug / Q parity): counts_out[g], then
  * [g][400] tile, visits, value_sum, prior. */
 int bk_selfplay_last_root(bk_selfplay* sp, int32_t* counts_out, int16_t* tile_out, uint32_t* visits_out,

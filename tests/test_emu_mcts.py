@@ -71,3 +71,20 @@ def test_emu_tree_reuse(emu_lib, orc):
                                                           dirichlet_alpha=0.3, exploration_fraction=0.25, seed=12),
                                           max_plies=8, xp="numpy")
     assert reuse < full
+
+
+def test_emu_packed_results_equal_per_game_records(emu_lib, orc):
+    """bk_selfplay_results_packed (one CSR gather) carries exactly the per-game policy records."""
+    import numpy as np
+    from blokus_self_play import SelfPlay, Config
+    sp = SelfPlay(3, Config(sims_per_move=10, sample_moves=2, c_base=19652, c_init=1.25, dirichlet_alpha=0.3,
+                            exploration_fraction=0.25, seed=8), first_game_id=2, lib=emu_lib)
+    sp.run_stub(5)
+    recs = sp.policy_records()
+    ply_off, ply_ptr, tiles, visits = sp.policy_records_packed()
+    assert ply_off.tolist() == [0, 5, 10, 15] and len(ply_ptr) == 16 and ply_ptr[-1] == len(tiles) == len(visits)
+    for g in range(3):
+        for k, (t, v) in enumerate(recs[g]):
+            a, b = ply_ptr[ply_off[g] + k], ply_ptr[ply_off[g] + k + 1]
+            assert np.array_equal(tiles[a:b], t) and np.array_equal(visits[a:b], v)
+    sp.close()

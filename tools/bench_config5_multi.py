@@ -44,6 +44,15 @@ c0 = sp.counters()
 ms = sp.run_stub(-1)    # every game of the shard to completion; CUDA events on the launching stream
 c1 = sp.counters()
 barrier()
+# gather the finished-game tuples on the host (north star: the only data that leaves the GPU): packed policy
+# records + packed histories + payoffs, timed on the host
+import time as _time
+_t = _time.perf_counter()
+_ply_off, _ply_ptr, _tiles, _visits = sp.policy_records_packed()
+_plies_h, _scores_h, _hist_h = sp.env.fetch()
+_pay = sp.env.payoff()
+gather_s = _time.perf_counter() - _t
+gather_bytes = _ply_ptr.nbytes + _tiles.nbytes + _visits.nbytes + _hist_h.nbytes + _plies_h.nbytes + _scores_h.nbytes + _pay.nbytes
 finished = int(sp.env.is_terminal().sum())
 payoff = sp.env.payoff()
 hists = sp.env.history()
@@ -75,20 +84,25 @@ if rank == 0:
     same = bool(np.array_equal(replay, mine))
     sp2.close()
 
-stats = torch.tensor([ms], dtype=torch.float64, device="cuda")
+stats = torch.tensor([ms, gather_s * 1e3, ms + gather_s * 1e3], dtype=torch.float64, device="cuda")
+gb = torch.tensor([float(gather_bytes)], dtype=torch.float64, device="cuda")
+if world > 1:
+    dist.all_reduce(gb, op=dist.ReduceOp.SUM)
 work = torch.tensor([c1["sims"] - c0["sims"], c1["applies"] - c0["applies"], n, finished, plies], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     dist.all_reduce(work, op=dist.ReduceOp.SUM)
 if rank == 0:
-    t = stats.item() * 1e-3
+    t = stats[0].item() * 1e-3
     sims, applies, games, fin, pl = work.tolist()
     print(json.dumps({
         "config": f"configs[4]: {int(games)} full self-play games sharded over {world} B200 ({n} per GPU, global game ids), "
                   f"{a.sims} sims/move, stub evaluator, to completion" + ("; forced-ply shortcut on" if a.skip_forced else ""),
         "n_gpus": world, "games": int(games), "finished": int(fin), "plies": int(pl), "sims": int(sims),
         "seconds_max_over_ranks": t, "games_per_s": games / t, "sims_per_s": sims / t, "moves_per_s": applies / t,
-        "training_tuples": "finished-game tuples stay per GPU (history + policy records + payoff); gathered on the host by the caller",
+        "host_gather": {"seconds_max_over_ranks": stats[1].item() * 1e-3, "bytes_all_ranks": gb.item(),
+                        "what": "packed policy records (bk_selfplay_results_packed) + packed histories + scores + payoffs into host memory, per GPU",
+                        "seconds_play_plus_gather": stats[2].item() * 1e-3, "games_per_s_incl_gather": games / (stats[2].item() * 1e-3)},
         "cross_check": {"ids": [ofirst, ofirst + k - 1], "owner_rank": owner, "replayed_on_rank": 0,
                         "identical_traces_and_payoffs": same}}), flush=True)
 if world > 1:
