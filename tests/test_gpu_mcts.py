@@ -149,3 +149,10 @@ def test_gpu_tree_reuse(cuda_lib, orc):
     full, reuse = parity.check_tree_reuse(cuda_lib, 6, dict(CONFIG3, sims_per_move=256, sample_moves=6, dirichlet_alpha=0.3, seed=21),
                                           max_plies=24, xp="torch")
     assert reuse < full
+
+
+def test_gpu_selfplay_config3_deep_prefix(cuda_lib, orc):
+    """BASELINE.json config 3 parameters (800 sims, alpha 0.03) carried 56 plies into a game — past the opening, where
+    roots have many children (the > 32-children select path), trees are deep and the narrowing cache is in every form —
+    every ply's root visit vector, the action trace and the last root's value sums against the oracle."""
+    parity.check_selfplay_stub(cuda_lib, orc, 8, CONFIG3, first_game_id=40, max_plies=56, n_check=1)
