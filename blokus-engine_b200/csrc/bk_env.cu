@@ -45,7 +45,10 @@ k_place_piece(BkState* __restrict__ states, uint16_t* __restrict__ hist, const i
 }
 
 // One warp per CTA: the hardware CTA scheduler balances games of different length over the SMs.
-__global__ void __launch_bounds__(32, 28)
+// MINB: resident CTAs (games) per SM the register allocation must allow: 28 covers BASELINE.json config 2 (4096 games =
+// 27.7 per SM) with 68 registers; larger batches use the 32-per-SM build (64 registers, the hardware's CTA limit).
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
           const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
           unsigned long long* counters) {
@@ -112,6 +115,12 @@ __global__ void k_legal_rows(const BkState* __restrict__ states, uint32_t* __res
 static int grid_for(int n, int warps) { return (n + warps - 1) / warps; }
 
 static int env_alloc_into(bk_env* e, int n_games, cudaStream_t stream) {
+#ifndef BK_WARP_EMU
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && sms > 0) e->num_sms = sms;
+    }
+#endif
     if (stream) { e->stream = stream; e->borrowed = true; }
     else BK_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     BK_CUDA(cudaMalloc(&e->d_states, sizeof(BkState) * size_t(n_games)));
@@ -419,8 +428,12 @@ static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const u
     }
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
-              flags, e->d_i32, e->d_hash, e->d_counters);
+    if (e->n > 28 * e->num_sms)
+        BK_LAUNCH(k_playout<32>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+                  flags, e->d_i32, e->d_hash, e->d_counters);
+    else
+        BK_LAUNCH(k_playout<28>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+                  flags, e->d_i32, e->d_hash, e->d_counters);
     return env_finish_timed(e, false);
 }
 

@@ -133,23 +133,31 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     BkPlayoutRng rng;
     rng.w0 = rng.w1 = rng.w2 = rng.w3 = 0u;
     rng.block = 0xffffffffu;
+    // While a turn is in progress the legal set lives in its 9x9-window form (warp-uniform words): counting and
+    // picking the idx-th tile are scalar there, and the board rows (G.legal) are only materialised on demand.
+    BkNarrow nw;
+    nw.w0 = nw.w1 = nw.w2 = 0u; nw.tr = nw.tc = 0; nw.pid = -1; nw.any_valid = false;
+    bool mid = false;                     // the loop starts from a stored state: its rows are valid
     while (!bk_terminal(G) && (max_plies < 0 || steps < max_plies)) {
-        const int cnt = bk_legal_count(G.legal);
+        const int cnt = mid ? bk_narrow_count(nw) : bk_legal_count(G.legal);
         int idx;
         if (flags & BK_PLAYOUT_MIN_TILE_FLAG) idx = 0;
         else if (flags & BK_PLAYOUT_MAX_TILE_FLAG) idx = cnt - 1;
         else idx = int(bk_playout_index(seed, game_id, G.ply, uint32_t(cnt), rng));
-        const int tile = bk_legal_select(G.legal, idx, lane);
+        const int tile = mid ? bk_narrow_select(nw, idx) : bk_legal_select(G.legal, idx, lane);
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;
-        if (!bk_apply(G, tile, -1, lane, tabs, ctr)) break;  // cannot happen: tile came from the legal set
+        if (!bk_apply_t<true>(G, tile, -1, lane, tabs, ctr, &nw)) break;  // cannot happen: tile came from the legal set
+        mid = ((G.meta >> 6) & 7u) != 0u;
         if (lane == 0 && ply < BK_HIST_CAP) h16[ply] = uint16_t(tile | (p << 9));
         if (flags & BK_PLAYOUT_HASH_FLAG) {
+            if (mid) G.legal = bk_narrow_row(nw, lane);
             h = bk_splitmix64(h ^ bk_digest(G, lane));
             h = bk_splitmix64(h ^ (uint64_t(p) | (uint64_t(tile) << 8)));
         }
         ++steps;
     }
+    if (mid) G.legal = bk_narrow_row(nw, lane);
     bk_store(&states[g], lane, G);
     if (lane == 0) { steps_out[g] = steps; hash_out[g] = h; }
     bk_flush_counters(ctr, uint32_t(steps), lane, counters);

@@ -183,9 +183,10 @@ __device__ __forceinline__ uint32_t bk_movegen_start(const BkRegs& G, int p, int
 }
 
 struct BkNarrow {
-    uint32_t legal;  // this lane's row of the narrowed legal set
-    int pid;         // piece id of a surviving placement (the committed piece when legal is empty)
-    bool any_valid;  // some turn-start placement contains T (always true after a legal tile)
+    uint32_t w0, w1, w2;  // the narrowed legal set inside the 9x9 window centred on T[0] = (tr, tc): warp-uniform
+    int tr, tc;
+    int pid;              // piece id of a surviving placement (the committed piece when the set is empty)
+    bool any_valid;       // some turn-start placement contains T (always true after a legal tile)
 };
 
 // window word index / bit of board tile t relative to the window centred on (tr, tc)
@@ -271,7 +272,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_first(BkRegs& G, uint32_t free_, u
     BkNarrow out;
     out.pid = found - 1;
     out.any_valid = found > 0;
-    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    out.w0 = L0; out.w1 = L1; out.w2 = L2; out.tr = tr; out.tc = tc;
     if ((L0 | L1 | L2) != 0u) bk_narrow_compact(G, lane, tabs);   // the turn goes on: later tiles re-test survivors
     return out;
 }
@@ -303,7 +304,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_next(BkRegs& G, int t0, int t, int
         BkNarrow out;
         out.pid = found - 1;
         out.any_valid = found > 0;
-        out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+        out.w0 = L0; out.w1 = L1; out.w2 = L2; out.tr = tr; out.tc = tc;
         return out;
     }
     const uint32_t* __restrict__ wk = k == 0 ? tabs.w0 : (k == 1 ? tabs.w1 : tabs.w2);
@@ -328,7 +329,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_next(BkRegs& G, int t0, int t, int
     BkNarrow out;
     out.pid = found - 1;
     out.any_valid = found > 0;
-    out.legal = bk_window_to_row(L0, L1, L2, tr, tc, lane);
+    out.w0 = L0; out.w1 = L1; out.w2 = L2; out.tr = tr; out.tc = tc;
     if ((L0 | L1 | L2) != 0u) bk_narrow_compact(G, lane, tabs);
     return out;
 }
@@ -373,13 +374,22 @@ __device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr)
 
 // Game::apply(tile, piece_to_finish) (game.rs:150-194).  finish < 0 is None.  Returns false (and
 // leaves the game untouched) when the tile is not legal or finish is out of range.
-__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
-                                         BkCounters& ctr) {
+// this lane's row of a narrowed legal set
+__device__ __forceinline__ uint32_t bk_narrow_row(const BkNarrow& nw, int lane) {
+    return bk_window_to_row(nw.w0, nw.w1, nw.w2, nw.tr, nw.tc, lane);
+}
+
+// TRUSTED_LAZY (the persistent playout only): the tile is known to come from the legal set, so the membership vote
+// is skipped, and while a turn is in progress G.legal is NOT refreshed — the caller works on the window form
+// returned through nw_out and materialises the rows (bk_narrow_row) when something needs them.
+template <bool TRUSTED_LAZY>
+__device__ __forceinline__ bool bk_apply_t(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
+                                           BkCounters& ctr, BkNarrow* nw_out) {
     if (tile < 0 || tile >= 400 || bk_terminal(G)) return false;
     const int p = bk_cur(G);
     const int tr = tile / 20, tc = tile % 20;
     const uint32_t bit = (lane == tr) ? (1u << tc) : 0u;
-    if (!__any_sync(BK_FULL, (G.legal & bit) != 0u)) return false;
+    if (!TRUSTED_LAZY && !__any_sync(BK_FULL, (G.legal & bit) != 0u)) return false;
     const uint32_t pieces = bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3);
     int fin_pid = -1;
     if (finish >= 0) {
@@ -403,7 +413,7 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
         bk_free_anchor(mine0, occ0, p, lane, free_, anch);
         nw = bk_narrow_first(G, free_, anch, pieces, tile, lane, tabs);
     }
-    const bool done = !__any_sync(BK_FULL, nw.legal != 0u);
+    const bool done = (nw.w0 | nw.w1 | nw.w2) == 0u;      // warp-uniform: no vote needed
     if (done || fin_pid >= 0) {
         // game.rs:176-191: commit the piece, remember its size, pass the turn
         const int pid = fin_pid >= 0 ? fin_pid : nw.pid;
@@ -415,14 +425,37 @@ __device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int la
         G.t01 = 0u; G.t23 = 0u;
         bk_advance(G, lane, ctr);
     } else {
-        G.legal = nw.legal;
+        if (!TRUSTED_LAZY) G.legal = bk_narrow_row(nw, lane);
         G.meta = (G.meta & ~(7u << 6)) | (uint32_t(nT) << 6);
         if (nT == 1) G.t01 = uint32_t(tile);
         else if (nT == 2) G.t01 |= uint32_t(tile) << 16;
         else if (nT == 3) G.t23 = uint32_t(tile);
         else G.t23 |= uint32_t(tile) << 16;
     }
+    if (nw_out) *nw_out = nw;
     return true;
+}
+
+__device__ __forceinline__ bool bk_apply(BkRegs& G, int tile, int finish, int lane, const BkTabs& tabs,
+                                         BkCounters& ctr) {
+    return bk_apply_t<false>(G, tile, finish, lane, tabs, ctr, nullptr);
+}
+
+// idx-th (0-based, ascending board order = window row-major order) tile of a narrowed legal set; warp-uniform
+// arithmetic on the window words, no collectives.  The sets are small (a handful of tiles), so the k-th set bit
+// is found by clearing the k lower ones.
+__device__ __forceinline__ int bk_narrow_count(const BkNarrow& nw) { return __popc(nw.w0) + __popc(nw.w1) + __popc(nw.w2); }
+__device__ __forceinline__ int bk_narrow_select(const BkNarrow& nw, int idx) {
+    const int c0 = __popc(nw.w0), c1 = __popc(nw.w1);
+    uint32_t w;
+    int base;
+    if (idx < c0) { w = nw.w0; base = 0; }
+    else if (idx < c0 + c1) { w = nw.w1; base = 27; idx -= c0; }
+    else { w = nw.w2; base = 54; idx -= c0 + c1; }
+    for (int i = 0; i < idx; ++i) w &= w - 1u;
+    const int bit = base + __ffs(w) - 1;
+    const int wr = bit / 9, wc = bit - 9 * wr;
+    return (nw.tr - 4 + wr) * 20 + (nw.tc - 4 + wc);
 }
 
 // Game::reset (game.rs:102-114)

@@ -29,6 +29,7 @@ int bk_fail(int code, const std::string& msg);
 struct bk_env {
     int n = 0;
     int device = 0;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     BkState* d_states = nullptr;
     uint16_t* d_hist = nullptr;      // [n][BK_HIST_CAP]: tile | player << 9
