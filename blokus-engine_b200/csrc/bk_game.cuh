@@ -246,7 +246,7 @@ __device__ __forceinline__ BkNarrow bk_narrow_first(BkRegs& G, uint32_t free_, u
     const uint32_t AW2 = __reduce_or_sync(BK_FULL, wk == 2 ? as << sh : 0u);
     uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = 0u;
     int found = 0;
-#pragma unroll
+#pragma unroll      // (a rolled loop measured 7 % slower in k_playout as well: 0.689 vs 0.647 ms)
     for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
         if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform: no piece of this chunk is held
         const int idx = ch * 32 + lane;
