@@ -711,6 +711,7 @@ __device__ __forceinline__ void kb_sp_begin(const BkSearchCfg& cfg, const BkStat
         if (live && !forced) bk_store(&tr.nodes[0], lane, G);
         if (forced) kind = BK_PEND_DONE;
     }
+    __syncwarp();                          // every lane has read the header before lane 0 rewrites it
     if (lane == 0) {
         hdr_g->n_nodes = hd.n_nodes; hdr_g->n_entries = hd.n_entries; hdr_g->root_visits = hd.root_visits;
         hdr_g->sims_done = hd.sims_done; hdr_g->forced_plies = hd.forced_plies; hdr_g->reused = hd.reused;
