@@ -156,3 +156,36 @@ def test_gpu_selfplay_config3_deep_prefix(cuda_lib, orc):
     roots have many children (the > 32-children select path), trees are deep and the narrowing cache is in every form —
     every ply's root visit vector, the action trace and the last root's value sums against the oracle."""
     parity.check_selfplay_stub(cuda_lib, orc, 8, CONFIG3, first_game_id=40, max_plies=56, n_check=1)
+
+
+def test_gpu_throughput_modes_at_config3_width(cuda_lib, orc):
+    """All three opt-in modes together at config 3's search size (800 sims) on 128 games for 12 plies through the
+    evaluator protocol (4 leaves per round, tree reuse, forced-ply shortcut), the evaluator being a device-side stub:
+    no pool overflows, every recorded policy sums to 800 visits, games advance; and complete games of the fused
+    kernel with tree reuse + shortcut finish with valid scores."""
+    import torch
+    from blokus_self_play import SelfPlay, Config, MODE_SKIP_FORCED, MODE_TREE_REUSE
+    cfg = Config(**CONFIG3)
+    sp = SelfPlay(128, cfg, lib=cuda_lib)
+    sp.set_mode(MODE_SKIP_FORCED | MODE_TREE_REUSE, 4)
+
+    def ev(planes):                                   # policy = legal mask, value = [0.4, 0.3, 0.2, 0.1]
+        n = planes.shape[0]
+        return planes[:, 4].reshape(n, 400).clone(), torch.tensor([0.4, 0.3, 0.2, 0.1], device=planes.device).repeat(n, 1)
+    info = sp.run_evaluator(ev, max_plies=12)
+    assert info["plies"] == 12
+    hist = sp.env.history()
+    for g, recs in enumerate(sp.policy_records()):
+        assert len(recs) == 12
+        for k, (tiles, visits) in enumerate(recs):
+            assert int(visits.sum()) == 800 and np.all(np.diff(tiles) > 0) and hist[g][k][1] in tiles.tolist()
+    sp.close()
+    full = SelfPlay(64, cfg, first_game_id=900, lib=cuda_lib)
+    full.set_mode(MODE_SKIP_FORCED | MODE_TREE_REUSE, 1)
+    full.run_stub(-1)
+    assert bool(full.env.is_terminal().all())
+    sc = full.env.scores()
+    assert sc.min() >= -89 and sc.max() <= 20
+    for recs in full.policy_records():
+        assert all(int(v.sum()) == 800 for _, v in recs)
+    full.close()
