@@ -260,6 +260,20 @@ class Game:
         mask = int(self._b.pieces()[0, self.current_player()])
         return [i for i in range(21) if (mask >> i) & 1]
 
+    def get_piece(self, player: int, piece: int, variant: int) -> dict:  # game.rs:234
+        """PieceVariant of the `piece`-th REMAINING piece of `player` (board.rs:147-153 list positions):
+        {"offsets": [...], "width": w, "len": variant.len(), "piece_id": id} (pieces.rs:58-98)."""
+        mask = int(self._b.pieces()[0, player])
+        ids = [i for i in range(21) if (mask >> i) & 1]
+        if not 0 <= piece < len(ids):
+            raise IndexError("piece index out of range of the player's remaining pieces")
+        w, n = C.c_int(0), C.c_int(0)
+        offs = (C.c_int * 5)()
+        k = self._b.lib.bk_piece_variant(ids[piece], variant, C.byref(w), C.byref(n), offs)
+        if k < 0:
+            raise IndexError("variant index out of range")
+        return {"offsets": list(offs[:k]), "width": w.value, "len": n.value, "piece_id": ids[piece]}
+
     @property
     def history(self):  # game.rs:94
         return self._b.history()[0]

@@ -118,9 +118,32 @@ public:
     bool is_player_active(int player) const { return b_.is_player_active()[size_t(player)] != 0; }
     std::vector<uint8_t> get_board_state() const { return b_.board_state(); }
     std::vector<std::pair<int, int>> history() const { return b_.history(0); }
+    // ids of the mover's remaining pieces in list order (game.rs:230; board.rs:147-153: indices into this list are
+    // what place_piece / apply(Some(p)) take)
+    std::vector<int> get_current_player_pieces() const { return remaining(current_player()); }
+    // PieceVariant of the `piece`-th remaining piece of `player` (game.rs:234): offsets of its squares and its width
+    struct PieceVariant { std::vector<int> offsets; int width = 0, len = 0, piece_id = 0; };
+    PieceVariant get_piece(int player, int piece, int variant) const {
+        const std::vector<int> ids = remaining(player);
+        if (piece < 0 || size_t(piece) >= ids.size()) throw Error(BK_ERR_INVALID_ARG, "piece index out of range");
+        PieceVariant pv;
+        int offs[5];
+        const int k = bk_piece_variant(ids[size_t(piece)], variant, &pv.width, &pv.len, offs);
+        if (k < 0) throw Error(k, bk_last_error());
+        pv.offsets.assign(offs, offs + k);
+        pv.piece_id = ids[size_t(piece)];
+        return pv;
+    }
     GameBatch& batch() { return b_; }
 
 private:
+    std::vector<int> remaining(int player) const {
+        std::vector<uint32_t> masks(4);
+        check(bk_env_pieces(b_.handle(), masks.data()));
+        std::vector<int> ids;
+        for (int i = 0; i < 21; ++i) if ((masks[size_t(player)] >> i) & 1u) ids.push_back(i);
+        return ids;
+    }
     GameBatch b_;
 };
 

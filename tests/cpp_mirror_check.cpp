@@ -24,7 +24,11 @@ int main() {
     bool ok = plies == 314 && sc[0] == 15 && sc[1] == -35 && sc[2] == -4 && sc[3] == -3 && g.history().size() == 314;
     blokus::Game h = blokus::Game::reset();
     try { h.apply(399); ok = false; } catch (const blokus::Error& e) { ok = ok && e.code == BK_ERR_ILLEGAL_MOVE; }
+    ok = ok && h.get_current_player_pieces().size() == 21;
+    const auto domino_v = h.get_piece(0, 1, 1);           // vertical domino: offsets {0, 20}, width 1 (pieces.rs:240-251)
+    ok = ok && domino_v.offsets.size() == 2 && domino_v.offsets[1] == 20 && domino_v.width == 1 && domino_v.len == 21;
     blokus::Game moved = h.place_piece(0, 0, 0);          // monomino on the start corner; h itself is untouched
+    ok = ok && moved.get_piece(0, 0, 0).piece_id == 1;    // player 0's list now starts with the domino
     ok = ok && h.history().empty() && moved.history().size() == 1 && moved.current_player() == 1;
     // self_play crate mirror: two stub self-play games, 24 simulations a move, six plies
     blokus::self_play::Config cfg;

@@ -35,3 +35,15 @@ def test_emu_place_piece(emu_lib, orc):
 
 def test_emu_piece_to_finish(emu_lib, orc):
     parity.check_piece_to_finish(emu_lib, orc, seed=4, n_steps=40)
+
+
+def test_emu_game_mirror_get_piece(emu_lib, orc):
+    """Game::get_piece / get_current_player_pieces (game.rs:230-236) of the Python mirror against the oracle's tables."""
+    from blokus_self_play import Game
+    g = Game.reset(lib=emu_lib)
+    assert g.get_current_player_pieces() == list(range(21))
+    pv = g.get_piece(0, 1, 1)
+    ref = orc.piece_variant(1, 1)
+    assert (pv["offsets"], pv["width"], pv["len"], pv["piece_id"]) == (ref["offsets"], ref["width"], ref["len"], 1)
+    g2 = g.place_piece(0, 0, 0)
+    assert g2.get_piece(0, 0, 0)["piece_id"] == 1 and g.get_piece(0, 0, 0)["piece_id"] == 0
