@@ -10,7 +10,7 @@
 // file passes all of them (tests/test_oracle_reference_kats.py).  Nothing in the reference pins
 // game.rs (apply / advance_player / scoring / planes): for those, "parity unpinned" — the
 // restatement is checked against the derived known answers of SURVEY.md Appendix C and against
-// an independent Python restatement (tests/golden/).  No Rust toolchain exists in this image,
+// an independently written second restatement (oracle/py_restatement.py, tests/test_py_restatement.py).  No Rust toolchain exists in this image,
 // so the reference itself cannot be run here.
 //
 // Canonicalisation: where the reference iterates a HashMap/HashSet the

@@ -10,7 +10,9 @@
 //   * rand::thread_rng() -> the seeded SPEC of rng_oracle.hpp;
 //   * the Python queue/pipe round trip (simulation.rs:50-57) -> an Evaluator callback with the same
 //     frames (planes rotated to the mover, policy in that frame, value in relative-seat order).
-// "Parity unpinned": the reference has no tests for this crate.
+// "Parity unpinned": the reference has no tests for this crate.  The noise-free core (evaluate,
+// ucb_score, select_child, backpropagate, mcts) is cross-checked bit for bit against an independently written second
+// restatement (oracle/py_restatement.py, tests/test_py_restatement.py).
 #pragma once
 #include <cmath>
 #include <functional>
