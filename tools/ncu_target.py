@@ -23,6 +23,14 @@ elif what == "conv":
         conv3x3(xp, w9, bias, xp, True, 1024, out=out)
     torch.cuda.synchronize()
     print("conv done")
+elif what == "mcts_big":
+    # config-5 regime: 8192 games per GPU (the 20-games-per-SM instantiation), opening plies
+    cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
+                 exploration_fraction=0.25, seed=1)
+    sp = SelfPlay(8192, cfg, max_children_per_game=16384)
+    for k in range(3):
+        ms = sp.run_stub(2)
+    print("mcts_big", sp.counters(), ms)
 elif what == "mcts_mid":
     # mid-game MCTS: 120 plies unprofiled, then 2-ply launches (profile the LAST: ncu -k regex:k_selfplay_stub -s 3 -c 1)
     cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
