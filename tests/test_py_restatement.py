@@ -105,3 +105,22 @@ def test_mcts_roots_agree(orc, which):
         action = R.best_action_by_visits(root)
         assert action == int(ref["tiles"][k])
         g.apply(action)
+
+
+def test_second_restatement_passes_the_reference_unit_tests():
+    """blokus/src/pieces.rs:225-301 and board.rs:213-225, against oracle/py_restatement.py as well."""
+    T, F = True, False
+    assert R.Piece(0).points == 1 and len(R.Piece(0).variants) == len(R.gen_variants([[T]]))
+    assert R.Piece(1).points == 2 and len(R.Piece(1).variants) == len(R.gen_variants([[T, T]]))
+    assert R.Piece(2).points == 3 and len(R.Piece(2).variants) == 4
+    assert R.Piece(19).points == 5 and len(R.Piece(19).variants) == 8
+    v = R.PieceVariant([[T]])
+    assert v.variant == [True] and v.offsets == [0] and v.width == 1
+    v = R.PieceVariant([[T], [T]])
+    assert len(v.variant) == 21 and v.offsets == [0, 20] and v.width == 1
+    assert R.rotate([[T, T]]) == [[T], [T]] and R.rotate([[T, T], [T, F]]) == [[T, T], [F, T]]
+    assert R.flip([[T, T]]) == [[T, T]] and R.flip([[T, T], [T, F]]) == [[T, T], [F, T]]
+    assert [len(R.gen_variants(s)) for s in ([[T, T]], [[T, T], [T, F]], [[T, T, T], [T, F, F]])] == [2, 4, 8]
+    b = R.Board()
+    assert len(b.board) == 400
+    assert b.is_valid_move(0, R.PieceVariant([[T, T]]), 0) is True and b.is_valid_move(0, R.PieceVariant([[T, T]]), 19) is False
