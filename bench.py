@@ -400,7 +400,9 @@ def main() -> int:
                        "games_per_gpu": n, "moves_per_step": moves / args.steps, "seed": SEED,
                        "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": "global game ids, rank r owns [r*n, (r+1)*n); no data-path collective"},
-            "gpu_launches": 2 * args.steps,
+            # kernels of this library launched inside the timed regions: device-resident steps (k_reset + k_playout) and
+            # end-to-end steps (k_reset + k_playout + k_scores); the MCTS and leaf-evaluation regions add theirs below
+            "gpu_launches": 2 * args.steps + 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                          "kernel": "k_playout", "launch_ms": launch_ms,
@@ -435,7 +437,7 @@ def main() -> int:
             }
         if leaf:
             flops = 18883996800.0 * MCTS_GAMES
-            line["gpu_launches"] += 41 * 13
+            line["gpu_launches"] += 41 * 10          # 41 hand-written convolutions per round, 10 timed rounds
             line["extra"]["leaf_eval"] = {
                 "metric": "resnet20x256_leaf_evals_per_sec", "value": MCTS_GAMES / (leaf["tcgen05"] * 1e-3), "unit": "leaves/s",
                 "config": "configs[3] building block: ResNet(20,256) random init, eval mode, 1024 leaves per round, one GPU; "
