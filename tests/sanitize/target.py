@@ -25,7 +25,10 @@ c = b.clone(); c.playout(seed=1, max_plies=9); c.playout(seed=1, max_plies=40 if
 cfg = Config(sims_per_move=12 if quick else 16, sample_moves=3, c_base=19652, c_init=1.25, dirichlet_alpha=0.3,
              exploration_fraction=0.25, seed=2)
 batched, _ = parity.fixed_network(1)
-for flags, k in ((0, 1), (MODE_SKIP_FORCED, 1), (MODE_TREE_REUSE, 1), (MODE_TREE_REUSE | MODE_SKIP_FORCED, 4), (0, 5)):
+MODES = ((0, 1), (MODE_SKIP_FORCED, 1), (MODE_TREE_REUSE, 1), (MODE_TREE_REUSE | MODE_SKIP_FORCED, 4), (0, 5))
+if quick:
+    MODES = ((0, 1), (MODE_TREE_REUSE, 1), (MODE_TREE_REUSE | MODE_SKIP_FORCED, 4))
+for flags, k in MODES:
     sp = SelfPlay(2 if quick else 3, cfg, lib=lib)
     sp.set_mode(flags, k)
     if k == 1:
