@@ -2,6 +2,7 @@
 // Host mirror of blokus/src/game.rs `Game`: every accessor of game.rs:196-311 has an entry point.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -45,10 +46,9 @@ k_place_piece(BkState* __restrict__ states, uint16_t* __restrict__ hist, const i
 }
 
 // One warp per CTA: the hardware CTA scheduler balances games of different length over the SMs.
-// MINB: resident CTAs (games) per SM the register allocation must allow: 28 covers BASELINE.json config 2 (4096 games =
-// 27.7 per SM) with 68 registers; larger batches use the 32-per-SM build (64 registers, the hardware's CTA limit).
-template <int MINB>
-__global__ void __launch_bounds__(32, MINB)
+// 32 CTAs (games) per SM is the hardware's CTA limit: 64 registers.  (A 28-per-SM build — 68 registers, enough for
+// config 2's 27.7 games per SM — measured the same on one batch and 2 % slower with two batches in flight.)
+__global__ void __launch_bounds__(32, 32)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
           const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
           unsigned long long* counters) {
@@ -428,12 +428,8 @@ static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const u
     }
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    if (e->n > 28 * e->num_sms)
-        BK_LAUNCH(k_playout<32>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
-                  flags, e->d_i32, e->d_hash, e->d_counters);
-    else
-        BK_LAUNCH(k_playout<28>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
-                  flags, e->d_i32, e->d_hash, e->d_counters);
+    BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+              flags, e->d_i32, e->d_hash, e->d_counters);
     return env_finish_timed(e, false);
 }
 
