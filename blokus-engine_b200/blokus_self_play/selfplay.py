@@ -155,8 +155,18 @@ class SelfPlay:
         return {"sims": int(c[0]), "applies": int(c[1]), "movegens": int(c[2]), "lane_ops": int(c[3]),
                 "entries": int(c[4]), "nodes": int(c[5])}
 
-    def policy_records(self, policy_cap: int = 32768):
-        """Per game, per searched ply: (tiles int16[k], visits uint32[k]) of the root's children."""
+    def policy_records(self):
+        """Per game, per searched ply: (tiles int16[k], visits uint32[k]) of the root's children (views into one packed
+        gather, bk_selfplay_results_packed)."""
+        ply_off, ply_ptr, tiles, visits = self.policy_records_packed()
+        out = []
+        for g in range(self.n):
+            a, b = int(ply_off[g]), int(ply_off[g + 1])
+            out.append([(tiles[ply_ptr[k]:ply_ptr[k + 1]], visits[ply_ptr[k]:ply_ptr[k + 1]]) for k in range(a, b)])
+        return out
+
+    def policy_records_unpacked(self, policy_cap: int = 32768):
+        """The same records through bk_selfplay_results (two copies per game into [n][policy_cap] host arrays)."""
         plies = np.zeros(self.n, dtype=np.int32)
         off = np.zeros((self.n, _lib.MAX_PLIES + 1), dtype=np.int32)
         tiles = np.zeros((self.n, policy_cap), dtype=np.int16)

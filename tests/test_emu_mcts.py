@@ -80,7 +80,7 @@ def test_emu_packed_results_equal_per_game_records(emu_lib, orc):
     sp = SelfPlay(3, Config(sims_per_move=10, sample_moves=2, c_base=19652, c_init=1.25, dirichlet_alpha=0.3,
                             exploration_fraction=0.25, seed=8), first_game_id=2, lib=emu_lib)
     sp.run_stub(5)
-    recs = sp.policy_records()
+    recs = sp.policy_records_unpacked()
     ply_off, ply_ptr, tiles, visits = sp.policy_records_packed()
     assert ply_off.tolist() == [0, 5, 10, 15] and len(ply_ptr) == 16 and ply_ptr[-1] == len(tiles) == len(visits)
     for g in range(3):
