@@ -189,3 +189,16 @@ def test_gpu_throughput_modes_at_config3_width(cuda_lib, orc):
     for recs in full.policy_records():
         assert all(int(v.sum()) == 800 for _, v in recs)
     full.close()
+
+
+def test_gpu_results_packed_equal_per_game_abi(cuda_lib, orc):
+    """bk_selfplay_results (per-game copies) and bk_selfplay_results_packed (one CSR gather) carry the same records."""
+    from blokus_self_play import SelfPlay, Config
+    sp = SelfPlay(40, Config(**dict(CONFIG3, sims_per_move=64)), first_game_id=9, lib=cuda_lib)
+    sp.run_stub(9)
+    a, b = sp.policy_records_unpacked(), sp.policy_records()
+    for ga, gb in zip(a, b):
+        assert len(ga) == len(gb) == 9
+        for (t1, v1), (t2, v2) in zip(ga, gb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    sp.close()
