@@ -257,6 +257,180 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     }
 }
 
+
+// ---- 2-SM variant (tcgen05 cta_group::2) ---------------------------------------------------------------------
+// The two CTAs of a cluster (one TPC) execute ONE UMMA of M = 256: each CTA supplies the A rows of its own
+// 128-row tile and HALF of the weight tile (128 of the 256 output channels), the tensor cores of both SMs read
+// the two halves from both shared memories, and each SM accumulates its own 128 rows in its own TMEM.  Per CTA
+// and pipeline step that is 16 KB A + 16 KB B of TMA traffic and shared-memory operand reads (the 1-SM kernel:
+// 16 + 32 KB fetched/received and read) — shared-memory bandwidth is what held the 1-SM kernel at ~80 % of the
+// UMMA issue floor.  Only the leader CTA (cluster rank 0) issues MMAs; both CTAs' TMA loads complete on the
+// LEADER's full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers;
+// both CTAs' epilogue warps hand the accumulator back on the leader's barrier.
+constexpr int kStages2 = 6;
+constexpr uint32_t kBytesBHalf = (kBlockN / 2) * kBlockK * 2;     // 16 KB
+constexpr uint32_t kBytesStage2 = kBytesA + kBytesBHalf;           // 32 KB
+constexpr uint32_t kSmemBytes2 = kStages2 * kBytesStage2 + 256 + 1024;
+constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kBlockN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc2), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+              int m_total, int n_tiles, int steps_per_tap, int relu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages2 * kBytesStage2;
+    auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(kStages2 + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * uint32_t(2 * kStages2 + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * uint32_t(2 * kStages2 + 2 + a); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStages2 * kBytesStage2 + 8 * (2 * kStages2 + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int steps = kTaps * steps_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }   // 4 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                              // both CTAs' barriers and TMEM exist before anyone signals a peer
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_holder;
+    const int crank = int(cluster_ctarank());
+    const bool leader = crank == 0;
+    const int n_groups = (n_tiles + 1) / 2;
+    const int first_group = int(blockIdx.x) / 2, group_stride = int(gridDim.x) / 2;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int grp = first_group; grp < n_groups; grp += group_stride) {
+                const int m0 = (grp * 2 + crank) * kBlockM;
+                for (int ks = 0; ks < steps; ++ks, ++it) {
+                    const int s = int(it % kStages2);
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);                       // freed in both CTAs by the leader's multicast commit
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * kBytesStage2);   // both CTAs' bytes complete on the leader's barrier
+                    const uint32_t lead_full = leader ? full_bar(s) : mapa_u32(full_bar(s), 0);
+                    const int tap = ks / steps_per_tap, kc = ks - tap * steps_per_tap;
+                    const int shift = (tap / 3 - 1) * kPadDim + (tap % 3 - 1);
+                    const uint32_t a_dst = smem_base + uint32_t(s) * kBytesStage2;
+                    tma_load_2d_2sm(a_dst, &map_x, lead_full, kc * kBlockK, m0 + shift);
+                    tma_load_2d_2sm(a_dst + kBytesA, &map_w, lead_full, kc * kBlockK, tap * kBlockN + crank * (kBlockN / 2));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            uint32_t it = 0, n_acc = 0;
+            for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+                const int acc = int(n_acc & 1u);
+                mbar_wait(tmem_empty_bar(acc), ((n_acc >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + uint32_t(acc) * kTmemCols;
+                for (int ks = 0; ks < steps; ++ks, ++it) {
+                    const int s = int(it % kStages2);
+                    const uint32_t ph = (it / kStages2) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_base + uint32_t(s) * kBytesStage2;
+                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + kBytesA);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_f16_2sm(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(empty_bar(s), uint16_t(3));            // frees the stage in both CTAs
+                }
+                umma_commit_2sm(tmem_full_bar(acc), uint16_t(3));          // accumulator complete, in both CTAs
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        uint32_t n_acc = 0;
+        for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+            const int acc = int(n_acc & 1u);
+            mbar_wait(tmem_full_bar(acc), (n_acc >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = (grp * 2 + crank) * kBlockM + wq * 32 + lane;
+            const int pos = m % kPadImage;
+            const bool live = m < m_total;
+            const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
+            uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
+            const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
+#pragma unroll 1
+            for (int cc = 0; cc < kBlockN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc) * kTmemCols + uint32_t(cc * 32), v);
+                if (!live) continue;
+                uint32_t packed[16];
+                if (pad) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                } else {
+                    uint4 r4[4];
+                    if (rrow) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                    }
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
+                        float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
+                        if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
+                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        packed[j] = pack_bf16(a, b);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {                                               // hand the accumulator back — on the LEADER's barrier
+                if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(acc)) : "memory");
+                else mbar_arrive_cluster(mapa_u32(tmem_empty_bar(acc), 0));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -300,7 +474,10 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     if (in_channels <= 0 || in_channels > kChannels || in_channels % kBlockK) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: in_channels must be 64, 128, 192 or 256");
     static int n_sm = 0;
     static int cluster = 2;
+    static int two_sm = 1;          // the cta_group::2 kernel (0.348 ms against 0.370 ms per convolution at batch 1024); BK_CONV_2SM=0 selects the 1-SM one
     if (!n_sm) {
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes2)));
+        if (const char* e = getenv("BK_CONV_2SM")) two_sm = atoi(e);
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
@@ -314,6 +491,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     CUtensorMap map_x, map_w;
     int rc = make_map(&map_x, dev_x, uint64_t(in_channels), uint64_t(m_total), kBlockM);
     if (rc) return rc;
+    if (two_sm) cluster = 2;
     rc = make_map(&map_w, dev_w, uint64_t(in_channels), uint64_t(kTaps) * kBlockN, uint32_t(kBlockN / cluster));
     if (rc) return rc;
     const int tiles = (m_total + kBlockM - 1) / kBlockM;
@@ -323,7 +501,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(n_clusters * cluster));
     cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = two_sm ? kSmemBytes2 : kSmemBytes;
     cfg.stream = static_cast<cudaStream_t>(cuda_stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -335,7 +513,8 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(dev_residual);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dev_y);
     const int spt = in_channels / kBlockK;
-    if (cluster == 1) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<1>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    if (two_sm) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    else if (cluster == 1) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<1>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (cluster == 2) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<2>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<4>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     BK_CUDA(cudaGetLastError());
