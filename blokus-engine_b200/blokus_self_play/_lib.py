@@ -162,5 +162,5 @@ _default = None
 def default_lib() -> Lib:
     global _default
     if _default is None:
-        _default = Lib(DEFAULT_LIB)
+        _default = Lib(os.environ.get("BK_LIB") or DEFAULT_LIB)     # BK_LIB: an alternative build of the same library (A/B probes)
     return _default
