@@ -591,6 +591,174 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
 }
 
+
+// ---- 2-SM variant with ONE A block per K-chunk for all nine taps -----------------------------------------------
+// The nine taps read row windows within [m0 - 22, m0 + 150): one 176-row block (22 swizzle atoms) per K-chunk
+// serves them all — tap (dy, dx) starts (dy+1)*21 + (dx+1) rows into it.  The A blocks live in their own 2-deep
+// ring (filled once per K-chunk), the weights in a 3-deep ring of (dy, K-chunk) stages (3 x 16 KB each), so the
+// per-CTA TMA traffic per K-chunk is 22 + 144 KB (the per-dy A blocks of k_conv3x3_tc3: 51 + 144 KB).
+constexpr int kRowsA4 = 176;
+constexpr uint32_t kBytesA4 = kRowsA4 * kBlockK * 2;               // 22 528
+constexpr uint32_t kBytesB4 = 3 * kBytesBHalf;                     // 49 152 per (dy, K-chunk) stage
+constexpr int kStagesA4 = 2, kStagesB4 = 3;
+constexpr uint32_t kSmemBytes4 = kStagesA4 * kBytesA4 + kStagesB4 * kBytesB4 + 256 + 1024;
+
+__global__ void __launch_bounds__(192, 1)
+k_conv3x3_tc4(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+              int m_total, int n_tiles, int steps_per_tap, int relu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t b_base = smem_base + kStagesA4 * kBytesA4;
+    const uint32_t bar_base = b_base + kStagesB4 * kBytesB4;
+    auto a_full = [&](int s) { return bar_base + 8u * uint32_t(s); };
+    auto a_empty = [&](int s) { return bar_base + 8u * uint32_t(2 + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * uint32_t(4 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * uint32_t(7 + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * uint32_t(10 + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * uint32_t(12 + a); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStagesA4 * kBytesA4 + kStagesB4 * kBytesB4 + 8 * 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStagesA4; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < kStagesB4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_holder;
+    const int crank = int(cluster_ctarank());
+    const bool leader = crank == 0;
+    const int n_groups = (n_tiles + 1) / 2;
+    const int first_group = int(blockIdx.x) / 2, group_stride = int(gridDim.x) / 2;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;                                   // A-block / B-stage counters across tiles
+            for (int grp = first_group; grp < n_groups; grp += group_stride) {
+                const int m0 = (grp * 2 + crank) * kBlockM;
+                for (int kc = 0; kc < steps_per_tap; ++kc, ++ia) {
+                    const int sa = int(ia % kStagesA4);
+                    mbar_wait(a_empty(sa), ((ia / kStagesA4) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(a_full(sa), 2 * kBytesA4);
+                    tma_load_2d_2sm(smem_base + uint32_t(sa) * kBytesA4, &map_x, leader ? a_full(sa) : mapa_u32(a_full(sa), 0),
+                                    kc * kBlockK, m0 - (kPadDim + 1));
+                    for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
+                        const int sb = int(ib % kStagesB4);
+                        mbar_wait(b_empty(sb), ((ib / kStagesB4) & 1u) ^ 1u);
+                        if (leader) mbar_expect_tx(b_full(sb), 2 * kBytesB4);
+                        const uint32_t lead_full = leader ? b_full(sb) : mapa_u32(b_full(sb), 0);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            tma_load_2d_2sm(b_base + uint32_t(sb) * kBytesB4 + uint32_t(dx) * kBytesBHalf, &map_w, lead_full, kc * kBlockK,
+                                            (dyi * 3 + dx) * kBlockN + crank * (kBlockN / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            uint32_t ia = 0, ib = 0, n_acc = 0;
+            for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+                const int acc = int(n_acc & 1u);
+                mbar_wait(tmem_empty_bar(acc), ((n_acc >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + uint32_t(acc) * kTmemCols;
+                for (int kc = 0; kc < steps_per_tap; ++kc, ++ia) {
+                    const int sa = int(ia % kStagesA4);
+                    mbar_wait(a_full(sa), (ia / kStagesA4) & 1u);
+                    const uint32_t a_addr = smem_base + uint32_t(sa) * kBytesA4;
+                    for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
+                        const int sb = int(ib % kStagesB4);
+                        mbar_wait(b_full(sb), (ib / kStagesB4) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t bs = b_base + uint32_t(sb) * kBytesB4;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint64_t da = umma_desc(a_addr + uint32_t(dyi * kPadDim + dx) * 128u);   // rows into the block
+                            const uint64_t db = umma_desc(bs + uint32_t(dx) * kBytesBHalf);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_f16_2sm(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), (kc > 0 || dyi > 0 || dx > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_2sm(b_empty(sb), uint16_t(3));
+                    }
+                    umma_commit_2sm(a_empty(sa), uint16_t(3));         // the A block is free once its 36 UMMAs have read it
+                }
+                umma_commit_2sm(tmem_full_bar(acc), uint16_t(3));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        uint32_t n_acc = 0;
+        for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+            const int acc = int(n_acc & 1u);
+            mbar_wait(tmem_full_bar(acc), (n_acc >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = (grp * 2 + crank) * kBlockM + wq * 32 + lane;
+            const int pos = m % kPadImage;
+            const bool live = m < m_total;
+            const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
+            uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
+            const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
+#pragma unroll 1
+            for (int cc = 0; cc < kBlockN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc) * kTmemCols + uint32_t(cc * 32), v);
+                if (!live) continue;
+                uint32_t packed[16];
+                if (pad) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                } else {
+                    uint4 r4[4];
+                    if (rrow) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                    }
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
+                        float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
+                        if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
+                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        packed[j] = pack_bf16(a, b);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(acc)) : "memory");
+                else mbar_arrive_cluster(mapa_u32(tmem_empty_bar(acc), 0));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
+    }
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -634,6 +802,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     if (in_channels <= 0 || in_channels > kChannels || in_channels % kBlockK) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: in_channels must be 64, 128, 192 or 256");
     static int n_sm = 0;
     static int cluster = 2;
+    static int a_reuse9 = 1;        // one A block per K-chunk for all nine taps: 0.305 ms per convolution at batch 1024 (BK_CONV_AREUSE9=0: per-dy blocks, 0.311)
     static int a_reuse = 1;         // the 2-SM kernel with one A block per (dy, K-chunk): 0.321 ms per convolution at batch 1024 (BK_CONV_AREUSE=0: 0.344)
     static int two_sm = 1;          // the cta_group::2 kernel (0.348 ms against 0.370 ms per convolution at batch 1024); BK_CONV_2SM=0 selects the 1-SM one
     if (!n_sm) {
@@ -641,6 +810,9 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
         if (const char* e = getenv("BK_CONV_2SM")) two_sm = atoi(e);
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes3)));
         if (const char* e = getenv("BK_CONV_AREUSE")) a_reuse = atoi(e);
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes4)));
+        if (const char* e = getenv("BK_CONV_AREUSE9")) a_reuse9 = atoi(e);
+        if (a_reuse9) a_reuse = 1;
         if (a_reuse) two_sm = 1;
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
@@ -653,7 +825,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     }
     const int m_total = batch * kPadImage;
     CUtensorMap map_x, map_w;
-    int rc = make_map(&map_x, dev_x, uint64_t(in_channels), uint64_t(m_total), a_reuse ? uint32_t(kRowsA3) : uint32_t(kBlockM));
+    int rc = make_map(&map_x, dev_x, uint64_t(in_channels), uint64_t(m_total), a_reuse9 ? uint32_t(kRowsA4) : (a_reuse ? uint32_t(kRowsA3) : uint32_t(kBlockM)));
     if (rc) return rc;
     if (two_sm) cluster = 2;
     rc = make_map(&map_w, dev_w, uint64_t(in_channels), uint64_t(kTaps) * kBlockN, uint32_t(kBlockN / cluster));
@@ -665,7 +837,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(n_clusters * cluster));
     cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = a_reuse ? kSmemBytes3 : (two_sm ? kSmemBytes2 : kSmemBytes);
+    cfg.dynamicSmemBytes = a_reuse9 ? kSmemBytes4 : a_reuse ? kSmemBytes3 : (two_sm ? kSmemBytes2 : kSmemBytes);
     cfg.stream = static_cast<cudaStream_t>(cuda_stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -677,7 +849,8 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(dev_residual);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dev_y);
     const int spt = in_channels / kBlockK;
-    if (a_reuse) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    if (a_reuse9) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc4, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    else if (a_reuse) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (two_sm) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (cluster == 1) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<1>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (cluster == 2) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<2>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
