@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace {
 
@@ -606,7 +607,7 @@ constexpr uint32_t kSmemBytes4 = kStagesA4 * kBytesA4 + kStagesB4 * kBytesB4 + 2
 __global__ void __launch_bounds__(192, 1)
 k_conv3x3_tc4(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-              int m_total, int n_tiles, int steps_per_tap, int relu) {
+              int m_total, int n_tiles, int steps_per_tap, int relu, int tile0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
@@ -648,7 +649,7 @@ k_conv3x3_tc4(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (lane == 0) {
             uint32_t ia = 0, ib = 0;                                   // A-block / B-stage counters across tiles
             for (int grp = first_group; grp < n_groups; grp += group_stride) {
-                const int m0 = (grp * 2 + crank) * kBlockM;
+                const int m0 = (tile0 + grp * 2 + crank) * kBlockM;
                 for (int kc = 0; kc < steps_per_tap; ++kc, ++ia) {
                     const int sa = int(ia % kStagesA4);
                     mbar_wait(a_empty(sa), ((ia / kStagesA4) & 1u) ^ 1u);
@@ -707,7 +708,7 @@ k_conv3x3_tc4(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             const int acc = int(n_acc & 1u);
             mbar_wait(tmem_full_bar(acc), (n_acc >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int m = (grp * 2 + crank) * kBlockM + wq * 32 + lane;
+            const int m = (tile0 + grp * 2 + crank) * kBlockM + wq * 32 + lane;
             const int pos = m % kPadImage;
             const bool live = m < m_total;
             const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
@@ -759,6 +760,197 @@ k_conv3x3_tc4(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }
 
 
+
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// barrier operand of the multicast weight loads: every destination CTA's PAIR LEADER must see the bytes.
+#ifndef BK_CONV5_BAR_MODE
+#define BK_CONV5_BAR_MODE 0
+#endif
+#if BK_CONV5_BAR_MODE == 0
+#define BK_CONV5_BAR(b) ((b) & 0xFEFFFFFFu)                       /* CTA-relative offset with the pair-peer bit cleared */
+#elif BK_CONV5_BAR_MODE == 1
+#define BK_CONV5_BAR(b) (leader ? (b) : mapa_u32((b), lead_rank)) /* explicit address of this CTA's pair leader */
+#else
+#define BK_CONV5_BAR(b) (b)
+#endif
+// ---- the same, in clusters of FOUR: the weight stream is shared by two CTA pairs ----------------------------------
+// CTAs 0/1 and 2/3 of a cluster are two MMA pairs working on different row tiles with the SAME weights: each CTA
+// fetches only a quarter of a weight tile (64 output channels) and TMA-multicasts it to the CTA of the other pair
+// that needs the same half (0 <-> 2, 1 <-> 3), so the per-CTA weight fetch halves (72 KB per K-chunk instead of 144).
+// A weight stage is recycled when BOTH pairs' MMAs have consumed it (both leaders' commits reach all four CTAs).
+// (text of the 2-CTA kernel follows)
+// ---- 2-SM variant with ONE A block per K-chunk for all nine taps
+// The nine taps read row windows within [m0 - 22, m0 + 150): one 176-row block (22 swizzle atoms) per K-chunk
+// serves them all — tap (dy, dx) starts (dy+1)*21 + (dx+1) rows into it.  The A blocks live in their own 2-deep
+// ring (filled once per K-chunk), the weights in a 3-deep ring of (dy, K-chunk) stages (3 x 16 KB each), so the
+// per-CTA TMA traffic per K-chunk is 22 + 144 KB (the per-dy A blocks of k_conv3x3_tc3: 51 + 144 KB).
+
+__global__ void __launch_bounds__(192, 1)
+k_conv3x3_tc5(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+              int m_total, int n_tiles, int steps_per_tap, int relu, int tile0) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t b_base = smem_base + kStagesA4 * kBytesA4;
+    const uint32_t bar_base = b_base + kStagesB4 * kBytesB4;
+    auto a_full = [&](int s) { return bar_base + 8u * uint32_t(s); };
+    auto a_empty = [&](int s) { return bar_base + 8u * uint32_t(2 + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * uint32_t(4 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * uint32_t(7 + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * uint32_t(10 + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * uint32_t(12 + a); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kStagesA4 * kBytesA4 + kStagesB4 * kBytesB4 + 8 * 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStagesA4; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < kStagesB4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_holder;
+    const int crank = int(cluster_ctarank());        // 0..3
+    const bool leader = (crank & 1) == 0;
+    const uint32_t lead_rank = uint32_t(crank & ~1);
+    const int half = crank & 1;                      // which half of the weight tile this CTA's pair member holds
+    const int quarter = crank >> 1;                  // which quarter of that half this CTA fetches
+    const uint16_t side_mask = uint16_t(0x5u << half);              // CTAs holding the same half: {0,2} or {1,3}
+    const uint16_t pair_mask = uint16_t(0x3u << (crank & ~1));      // this CTA's MMA pair
+    const int n_groups = (n_tiles + 3) / 4;
+    const int first_group = int(blockIdx.x) / 4, group_stride = int(gridDim.x) / 4;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;                                   // A-block / B-stage counters across tiles
+            for (int grp = first_group; grp < n_groups; grp += group_stride) {
+                const int m0 = (tile0 + grp * 4 + crank) * kBlockM;
+                for (int kc = 0; kc < steps_per_tap; ++kc, ++ia) {
+                    const int sa = int(ia % kStagesA4);
+                    mbar_wait(a_empty(sa), ((ia / kStagesA4) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(a_full(sa), 2 * kBytesA4);
+                    tma_load_2d_2sm(smem_base + uint32_t(sa) * kBytesA4, &map_x, leader ? a_full(sa) : mapa_u32(a_full(sa), lead_rank),
+                                    kc * kBlockK, m0 - (kPadDim + 1));
+                    for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
+                        const int sb = int(ib % kStagesB4);
+                        mbar_wait(b_empty(sb), ((ib / kStagesB4) & 1u) ^ 1u);
+                        if (leader) mbar_expect_tx(b_full(sb), 2 * kBytesB4);
+                        const uint32_t lead_full = BK_CONV5_BAR(b_full(sb));
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            tma_load_2d_2sm_mc(b_base + uint32_t(sb) * kBytesB4 + uint32_t(dx) * kBytesBHalf + uint32_t(quarter) * (kBytesBHalf / 2),
+                                               &map_w, lead_full, kc * kBlockK,
+                                               (dyi * 3 + dx) * kBlockN + half * (kBlockN / 2) + quarter * (kBlockN / 4), side_mask);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            uint32_t ia = 0, ib = 0, n_acc = 0;
+            for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+                const int acc = int(n_acc & 1u);
+                mbar_wait(tmem_empty_bar(acc), ((n_acc >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + uint32_t(acc) * kTmemCols;
+                for (int kc = 0; kc < steps_per_tap; ++kc, ++ia) {
+                    const int sa = int(ia % kStagesA4);
+                    mbar_wait(a_full(sa), (ia / kStagesA4) & 1u);
+                    const uint32_t a_addr = smem_base + uint32_t(sa) * kBytesA4;
+                    for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
+                        const int sb = int(ib % kStagesB4);
+                        mbar_wait(b_full(sb), (ib / kStagesB4) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t bs = b_base + uint32_t(sb) * kBytesB4;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint64_t da = umma_desc(a_addr + uint32_t(dyi * kPadDim + dx) * 128u);   // rows into the block
+                            const uint64_t db = umma_desc(bs + uint32_t(dx) * kBytesBHalf);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_f16_2sm(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), (kc > 0 || dyi > 0 || dx > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_2sm(b_empty(sb), uint16_t(0xF));              // all four CTAs: both pairs share the stage
+                    }
+                    umma_commit_2sm(a_empty(sa), pair_mask);         // the A block is free once its 36 UMMAs have read it
+                }
+                umma_commit_2sm(tmem_full_bar(acc), pair_mask);
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        uint32_t n_acc = 0;
+        for (int grp = first_group; grp < n_groups; grp += group_stride, ++n_acc) {
+            const int acc = int(n_acc & 1u);
+            mbar_wait(tmem_full_bar(acc), (n_acc >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = (tile0 + grp * 4 + crank) * kBlockM + wq * 32 + lane;
+            const int pos = m % kPadImage;
+            const bool live = m < m_total;
+            const bool pad = (pos / kPadDim == kPadDim - 1) || (pos % kPadDim == kPadDim - 1);
+            uint4* orow = reinterpret_cast<uint4*>(out + size_t(m) * kChannels);
+            const uint4* rrow = residual ? reinterpret_cast<const uint4*>(residual + size_t(m) * kChannels) : nullptr;
+#pragma unroll 1
+            for (int cc = 0; cc < kBlockN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(wq * 32) << 16) + uint32_t(acc) * kTmemCols + uint32_t(cc * 32), v);
+                if (!live) continue;
+                uint32_t packed[16];
+                if (pad) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                } else {
+                    uint4 r4[4];
+                    if (rrow) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) r4[q] = rrow[cc * 4 + q];
+                    }
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r4);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(v[2 * j]) + bias[cc * 32 + 2 * j];
+                        float b = __uint_as_float(v[2 * j + 1]) + bias[cc * 32 + 2 * j + 1];
+                        if (rrow) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
+                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        packed[j] = pack_bf16(a, b);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    orow[cc * 4 + q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(acc)) : "memory");
+                else mbar_arrive_cluster(mapa_u32(tmem_empty_bar(acc), lead_rank));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
+    }
+}
+
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -802,6 +994,11 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     if (in_channels <= 0 || in_channels > kChannels || in_channels % kBlockK) return bk_fail(BK_ERR_INVALID_ARG, "bk_conv3x3_bf16: in_channels must be 64, 128, 192 or 256");
     static int n_sm = 0;
     static int cluster = 2;
+    // BK_CONV_QUAD=1: clusters of four, the weight stream multicast across the two CTA pairs.  Correct, and 6.5 % faster
+    // per SM, but only 33 clusters of four are co-resident on the 148 SMs (a cluster must fit inside a GPC), so 16 SMs
+    // idle: 0.321 ms per convolution against 0.305 ms for the pair kernel.  (Running CTA pairs on the left-over SMs from a
+    // second stream did not overlap with the cluster-of-four kernel.)  Kept as an option.
+    static int quad = 0;
     static int a_reuse9 = 1;        // one A block per K-chunk for all nine taps: 0.305 ms per convolution at batch 1024 (BK_CONV_AREUSE9=0: per-dy blocks, 0.311)
     static int a_reuse = 1;         // the 2-SM kernel with one A block per (dy, K-chunk): 0.321 ms per convolution at batch 1024 (BK_CONV_AREUSE=0: 0.344)
     static int two_sm = 1;          // the cta_group::2 kernel (0.348 ms against 0.370 ms per convolution at batch 1024); BK_CONV_2SM=0 selects the 1-SM one
@@ -811,7 +1008,10 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes3)));
         if (const char* e = getenv("BK_CONV_AREUSE")) a_reuse = atoi(e);
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes4)));
-        if (const char* e = getenv("BK_CONV_AREUSE9")) a_reuse9 = atoi(e);
+        BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes4)));
+        if (const char* e = getenv("BK_CONV_QUAD")) quad = atoi(e);
+        if (quad) { a_reuse9 = 1; }
+        if (const char* e = getenv("BK_CONV_AREUSE9")) a_reuse9 = quad ? 1 : atoi(e);
         if (a_reuse9) a_reuse = 1;
         if (a_reuse) two_sm = 1;
         BK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
@@ -828,6 +1028,7 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     int rc = make_map(&map_x, dev_x, uint64_t(in_channels), uint64_t(m_total), a_reuse9 ? uint32_t(kRowsA4) : (a_reuse ? uint32_t(kRowsA3) : uint32_t(kBlockM)));
     if (rc) return rc;
     if (two_sm) cluster = 2;
+    if (quad) cluster = 4;
     rc = make_map(&map_w, dev_w, uint64_t(in_channels), uint64_t(kTaps) * kBlockN, uint32_t(kBlockN / cluster));
     if (rc) return rc;
     const int tiles = (m_total + kBlockM - 1) / kBlockM;
@@ -846,10 +1047,25 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (quad) {
+        // clusters of four must fit inside a GPC, so fewer than n_sm / 4 may be co-resident: a persistent grid larger
+        // than that would run its last clusters after the others
+        static int max_quads = 0;
+        if (!max_quads) {
+            cfg.gridDim = dim3(unsigned((n_sm / 4) * 4));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc5, &cfg) == cudaSuccess && n > 0) max_quads = n;
+            else max_quads = n_sm / 4;
+            if (getenv("BK_CONV_DEBUG")) fprintf(stderr, "bk_conv: %d clusters of 4 can be co-resident on %d SMs\n", max_quads, n_sm);
+        }
+        if (n_clusters > max_quads) n_clusters = max_quads;
+        cfg.gridDim = dim3(unsigned(n_clusters * cluster));
+    }
     const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(dev_residual);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dev_y);
     const int spt = in_channels / kBlockK;
-    if (a_reuse9) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc4, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
+    if (quad) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc5, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu, 0));
+    else if (a_reuse9) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc4, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu, 0));
     else if (a_reuse) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (two_sm) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (cluster == 1) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc<1>, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
