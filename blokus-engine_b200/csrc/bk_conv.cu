@@ -996,8 +996,8 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     static int cluster = 2;
     // BK_CONV_QUAD=1: clusters of four, the weight stream multicast across the two CTA pairs.  Correct, and 6.5 % faster
     // per SM, but only 33 clusters of four are co-resident on the 148 SMs (a cluster must fit inside a GPC), so 16 SMs
-    // idle: 0.321 ms per convolution against 0.305 ms for the pair kernel.  (Running CTA pairs on the left-over SMs from a
-    // second stream did not overlap with the cluster-of-four kernel.)  Kept as an option.
+    // idle: 0.321 ms per convolution against 0.305 ms for the pair kernel.  With CTA pairs on the left-over SMs from a second
+    // stream (the hybrid below; BK_CONV_QUAD_ONLY=1 disables it) the launch ties with the pair kernel (0.306 ms).  An option.
     static int quad = 0;
     static int a_reuse9 = 1;        // one A block per K-chunk for all nine taps: 0.305 ms per convolution at batch 1024 (BK_CONV_AREUSE9=0: per-dy blocks, 0.311)
     static int a_reuse = 1;         // the 2-SM kernel with one A block per (dy, K-chunk): 0.321 ms per convolution at batch 1024 (BK_CONV_AREUSE=0: 0.344)
@@ -1064,7 +1064,43 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
     const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(dev_residual);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dev_y);
     const int spt = in_channels / kBlockK;
-    if (quad) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc5, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu, 0));
+    if (quad) {
+        // Hybrid: clusters of four on the SMs that can host them, CTA pairs (second stream, concurrently) on the SMs
+        // left over in each GPC; the tiles are split in proportion to the two grids' per-SM speeds.
+        static cudaStream_t side = nullptr;
+        static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        if (!side) {
+            BK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            BK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            BK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        const int quad_sms = n_clusters * 4;
+        const int rest_pairs = (n_sm - quad_sms) / 2;
+        int tiles_pair = 0;
+        if (rest_pairs > 0 && tiles > 8 * n_sm && !getenv("BK_CONV_QUAD_ONLY")) {
+            const double share = (2.0 * rest_pairs) / (2.0 * rest_pairs + 1.065 * quad_sms);
+            tiles_pair = (int(share * tiles) / 2) * 2;
+        }
+        const int tiles_quad = tiles - tiles_pair;
+        if (tiles_pair > 0) BK_CUDA(cudaEventRecord(ev_fork, cfg.stream));      // fork BEFORE the first kernel is enqueued
+        BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc5, map_x, map_w, dev_bias, res, y, m_total, tiles_quad, spt, relu, 0));
+        if (tiles_pair > 0) {
+            CUtensorMap map_w2;                                                // weight map with 128-row boxes for the pair kernel
+            rc = make_map(&map_w2, dev_w, uint64_t(in_channels), uint64_t(kTaps) * kBlockN, uint32_t(kBlockN / 2));
+            if (rc) return rc;
+            BK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            cudaLaunchConfig_t cfg2 = cfg;
+            cudaLaunchAttribute attr2[1];
+            attr2[0] = attr[0];
+            attr2[0].val.clusterDim.x = 2;
+            cfg2.attrs = attr2;
+            cfg2.gridDim = dim3(unsigned(rest_pairs * 2));
+            cfg2.stream = side;
+            BK_CUDA(cudaLaunchKernelEx(&cfg2, k_conv3x3_tc4, map_x, map_w2, dev_bias, res, y, m_total, tiles_pair, spt, relu, tiles_quad));
+            BK_CUDA(cudaEventRecord(ev_join, side));
+            BK_CUDA(cudaStreamWaitEvent(cfg.stream, ev_join, 0));
+        }
+    }
     else if (a_reuse9) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc4, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu, 0));
     else if (a_reuse) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
     else if (two_sm) BK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, map_x, map_w, dev_bias, res, y, m_total, tiles, spt, relu));
