@@ -1078,7 +1078,8 @@ static int conv_launch(const void* dev_x, const void* dev_w, const float* dev_bi
         const int rest_pairs = (n_sm - quad_sms) / 2;
         int tiles_pair = 0;
         if (rest_pairs > 0 && tiles > 8 * n_sm && !getenv("BK_CONV_QUAD_ONLY")) {
-            const double share = (2.0 * rest_pairs) / (2.0 * rest_pairs + 1.065 * quad_sms);
+            double share = (2.0 * rest_pairs) / (2.0 * rest_pairs + 1.065 * quad_sms);
+            if (const char* e = getenv("BK_CONV_PAIR_SHARE")) share = atof(e);       // probes
             tiles_pair = (int(share * tiles) / 2) * 2;
         }
         const int tiles_quad = tiles - tiles_pair;
