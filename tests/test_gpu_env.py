@@ -94,3 +94,28 @@ def test_gpu_max_plies_prefix(cuda_lib, orc):
     b = GameBatch(64, lib=cuda_lib)
     b.playout(seed=9)
     assert np.array_equal(a.digest(), b.digest()) and a.history() == b.history()
+
+
+def test_gpu_playout_65536_games(cuda_lib, orc):
+    """16x BASELINE.json config 2's width in one launch: every game ends, scores stay in the rules' range, plies in the
+    survey's band, and trace hashes of games spread over the batch equal the oracle's; a resume from a mid-turn cut
+    (the playout loop's window-form legal set has to be materialised at the cut) gives the same games."""
+    from blokus_self_play import GameBatch, PLAYOUT_HASH
+    n, seed = 65536, 4242
+    b = GameBatch(n, lib=cuda_lib)
+    r = b.playout(seed=seed, flags=PLAYOUT_HASH)
+    assert bool(b.is_terminal().all())
+    sc = b.scores()
+    assert sc.min() >= -89 and sc.max() <= 20
+    assert 180 <= int(r["steps"].min()) and int(r["steps"].max()) <= 340 and abs(float(r["steps"].mean()) - 272.9) < 3
+    extremes = (int(np.argmin(r["steps"])), int(np.argmax(r["steps"])))      # the shortest and the longest game of the batch
+    for g in (0, 1, 4095, 4096, 32768, 65535) + extremes:
+        ref = orc.playout(seed, g, 0)
+        assert ref["n_plies"] == int(r["steps"][g]) and ref["hash"] == int(r["hash"][g]) and list(ref["scores"]) == sc[g].tolist()
+    digest = b.digest()
+    c = GameBatch(n, lib=cuda_lib)
+    c.playout(seed=seed, max_plies=37)          # most games are mid-turn after 37 tiles
+    c.playout(seed=seed, max_plies=1)
+    c.playout(seed=seed)
+    assert np.array_equal(c.digest(), digest)
+    b.close(); c.close()
