@@ -208,11 +208,14 @@ public:
     }
     std::vector<TrainingGame> results() const {
         const size_t n = static_cast<size_t>(n_);
-        const int32_t cap = 32768;
-        std::vector<int32_t> plies(n), off(n * (BK_MAX_PLIES + 1));
-        std::vector<int16_t> tile(n * size_t(cap));
-        std::vector<uint32_t> visits(n * size_t(cap));
-        check(bk_selfplay_results(sp_, plies.data(), off.data(), cap, tile.data(), visits.data()));
+        // one packed (compressed-row) gather of every game's policy records
+        int64_t total_plies = 0, total_entries = 0;
+        std::vector<int64_t> ply_off(n + 1);
+        check(bk_selfplay_results_sizes(sp_, &total_plies, &total_entries, ply_off.data(), nullptr));
+        std::vector<int64_t> ply_ptr(size_t(total_plies) + 1);
+        std::vector<int16_t> tile(size_t(total_entries) + 1);
+        std::vector<uint32_t> visits(size_t(total_entries) + 1);
+        check(bk_selfplay_results_packed(sp_, ply_ptr.data(), tile.data(), visits.data()));
         bk_env* env = bk_selfplay_env(sp_);
         std::vector<int32_t> cnt(n), pl(n * BK_MAX_PLIES), tl(n * BK_MAX_PLIES);
         check(bk_env_history(env, cnt.data(), pl.data(), tl.data()));
@@ -222,13 +225,13 @@ public:
         for (size_t g = 0; g < n; ++g) {
             TrainingGame& t = out[g];
             for (int i = 0; i < cnt[g]; ++i) t.history.emplace_back(pl[g * BK_MAX_PLIES + size_t(i)], tl[g * BK_MAX_PLIES + size_t(i)]);
-            for (int k = 0; k < plies[g]; ++k) {
-                const int32_t a = off[g * (BK_MAX_PLIES + 1) + size_t(k)], b = off[g * (BK_MAX_PLIES + 1) + size_t(k) + 1];
+            for (int64_t k = ply_off[g]; k < ply_off[g + 1]; ++k) {
+                const int64_t a = ply_ptr[size_t(k)], b = ply_ptr[size_t(k) + 1];
                 uint32_t total = 0;
-                for (int32_t e = a; e < b; ++e) total += visits[g * size_t(cap) + size_t(e)];
+                for (int64_t e = a; e < b; ++e) total += visits[size_t(e)];
                 std::vector<std::pair<int, float>> pol;
-                for (int32_t e = a; e < b; ++e)                                           // simulation.rs:222
-                    pol.emplace_back(int(tile[g * size_t(cap) + size_t(e)]), float(visits[g * size_t(cap) + size_t(e)]) / float(total));
+                for (int64_t e = a; e < b; ++e)                                           // simulation.rs:222
+                    pol.emplace_back(int(tile[size_t(e)]), float(visits[size_t(e)]) / float(total));
                 t.policies.push_back(std::move(pol));
             }
             t.values.assign(pay.begin() + long(g) * 4, pay.begin() + long(g) * 4 + 4);
