@@ -176,3 +176,50 @@ def test_gpu_serving_matches_reference_server_math(cuda_lib):
     assert np.all(np.asarray(out["policy"])[~legal] == 0) and abs(sum(out["policy"]) - 1.0) < 1e-4
     many = serving.process_requests([req] * 3, LeafEvaluator(model))
     assert len(many) == 3 and np.allclose(many[2]["policy"], out["policy"], atol=1e-6)
+
+
+def test_replay_buffer_ring_and_sampling():
+    """Row f1's consumer: the device-resident replay buffer (torchrl ReplayBuffer stand-in, training.py:114-129) — ring
+    semantics and sampling, on CPU tensors here (it is plumbing; the GPU test feeds it from training_tensors)."""
+    from blokus_self_play.replay import DeviceReplayBuffer
+    buf = DeviceReplayBuffer(capacity=10, batch_size=4, device="cpu", seed=1)
+    mk = lambda a, b: {"states": (torch.arange(a, b).view(-1, 1, 1, 1) % 2).expand(-1, 5, 20, 20).float(),
+                       "policies": torch.arange(a, b).float().view(-1, 1).expand(-1, 400).contiguous(),
+                       "scores": torch.arange(a, b).float().view(-1, 1).expand(-1, 4).contiguous()}
+    buf.extend(mk(0, 6))
+    assert len(buf) == 6 and buf.cursor == 6
+    buf.extend(mk(6, 13))                         # wraps: slots hold samples 3..12
+    assert len(buf) == 10 and buf.cursor == 3
+    assert sorted(buf.scores[:, 0].tolist()) == [float(x) for x in range(3, 13)]
+    s = buf.sample()
+    assert s.get("states").shape == (4, 5, 20, 20) and s.get("states").dtype == torch.float32
+    assert s.get("policies").shape == (4, 400) and s.get("scores").shape == (4, 4)
+    assert torch.equal(s.get("policies")[:, 0], s.get("scores")[:, 0])          # rows stay aligned
+    assert torch.equal(s.get("states")[:, 0, 0, 0], s.get("scores")[:, 0] % 2)
+    buf.extend(mk(100, 125))                      # more than the capacity at once: the newest 10 stay
+    assert sorted(buf.scores[:, 0].tolist()) == [float(x) for x in range(115, 125)]
+
+
+@pytest.mark.gpu
+def test_gpu_replay_buffer_from_selfplay(cuda_lib, orc):
+    """Self-play -> training tensors -> replay buffer -> one optimiser step of the reference's train() (training.py:122-142),
+    all on the device."""
+    from blokus_self_play import SelfPlay, Config
+    from blokus_self_play.replay import DeviceReplayBuffer
+    from blokus_self_play.resnet import ResNet
+    sp = SelfPlay(8, Config(sims_per_move=16, sample_moves=4, c_base=19652, c_init=1.25, dirichlet_alpha=0.3,
+                            exploration_fraction=0.25, seed=3), lib=cuda_lib)
+    sp.run_stub(10)
+    buf = DeviceReplayBuffer(capacity=64, batch_size=32, device="cuda", seed=0)
+    assert buf.extend_from(sp) == 80 and len(buf) == 64
+    batch = buf.sample()
+    st, po, sc = batch.get("states"), batch.get("policies"), batch.get("scores")
+    assert st.is_cuda and st.shape == (32, 5, 20, 20) and set(st.unique().tolist()) <= {0.0, 1.0}
+    assert torch.allclose(po.sum(dim=1), torch.ones(32, device="cuda"), atol=1e-5)
+    assert torch.all((po > 0) <= (st[:, 4].reshape(32, 400) > 0))              # policy mass only on the recorded legal tiles
+    model = ResNet(2, 16).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    policy, value = model(st)
+    loss = torch.nn.functional.cross_entropy(policy, po) + torch.nn.functional.mse_loss(value, sc)
+    loss.backward(); opt.step()
+    assert torch.isfinite(loss)
