@@ -223,3 +223,16 @@ def test_gpu_replay_buffer_from_selfplay(cuda_lib, orc):
     loss = torch.nn.functional.cross_entropy(policy, po) + torch.nn.functional.mse_loss(value, sc)
     loss.backward(); opt.step()
     assert torch.isfinite(loss)
+
+
+@pytest.mark.gpu
+def test_gpu_training_rounds_script(cuda_lib):
+    """tools/train_rounds.py — the reference's main() (training.py:176-229) on this engine — runs two tiny rounds."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "train_rounds.py"), "--games", "6", "--sims", "8", "--max-plies", "6",
+                        "--training-steps", "3", "--batch-size", "16", "--leaves", "2", "--skip-forced"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2 and lines[1]["buffer"] == 72 and lines[1]["steps"] == 6
+    assert all(l["new_samples"] == 36 and l["policy_loss"] == l["policy_loss"] for l in lines)   # 6 games x 6 plies, finite losses
