@@ -104,6 +104,7 @@ _SIGNATURES = {
     "bk_selfplay_begin_ply": (C.c_int, [_P]),
     "bk_selfplay_leaf_planes": (C.c_int, [_P, _P, _P]),
     "bk_selfplay_expand_backup": (C.c_int, [_P, _P, _P, _P]),
+    "bk_selfplay_leaf_rows": (C.c_int, [_P, _P]),
     "bk_selfplay_end_ply": (C.c_int, [_P]),
     "bk_selfplay_set_stream": (C.c_int, [_P, _P]),
     "bk_selfplay_set_mode": (C.c_int, [_P, C.c_uint32, C.c_int]),

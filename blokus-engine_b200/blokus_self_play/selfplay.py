@@ -94,6 +94,13 @@ class SelfPlay:
         self.lib.check(self.lib.bk_selfplay_leaf_planes(self._h, C.c_void_p(dev_planes_ptr), C.byref(cnt) if want_count else None))
         return cnt.value
 
+    def leaf_rows(self) -> int:
+        """Rows of the evaluator batch written by the last leaf_planes(): n in the exact mode, the number of leaves
+        outstanding (dense rows) in the multi-leaf mode."""
+        v = C.c_int32(0)
+        self.lib.check(self.lib.bk_selfplay_leaf_rows(self._h, C.byref(v)))
+        return v.value
+
     def expand_backup(self, dev_policy_ptr: int, dev_value_ptr: int, want_count: bool = True) -> int:
         cnt = C.c_int32(0)
         self.lib.check(self.lib.bk_selfplay_expand_backup(self._h, C.c_void_p(dev_policy_ptr), C.c_void_p(dev_value_ptr),
@@ -106,12 +113,14 @@ class SelfPlay:
     def run_evaluator(self, evaluator: Callable, max_plies: int = -1, xp: str = "torch") -> dict:
         """training_game() for every client with a caller-supplied evaluator.
 
-        evaluator(planes[n,5,20,20] float32) -> (policy[n,400] float32 in the mover's frame, value[n,4] float32
+        evaluator(planes[R,5,20,20] float32) -> (policy[R,400] float32 in the mover's frame, value[R,4] float32
         in relative-seat order), exactly the contract of the reference's inference server
-        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch (n = games x leaves_per_round).
+        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch: R = n games in the exact mode
+        (row g = game g), R = the leaves outstanding in the multi-leaf mode (dense rows, at most n x leaves_per_round).
         xp="torch": CUDA tensors on this handle's device; xp="numpy": host arrays, valid only with the tests'
         CPU-emulator build of the library (where "device" memory is host memory)."""
-        n = self.n * self.leaves_per_round      # slot j of game g is row g * K + j; unused slots are zero planes
+        n = self.n * self.leaves_per_round      # capacity of the evaluator batch
+        dense = self.leaves_per_round > 1 or bool(self.mode & _lib.MODE_FORCE_MULTI_LEAF)
         if xp == "torch":
             import torch
             dev = torch.device("cuda", self.env.device)
@@ -129,8 +138,13 @@ class SelfPlay:
             self.begin_ply()
             pending = self.leaf_planes(ptr(planes))
             while pending > 0:
-                policy, value = evaluator(planes)
-                policy, value = prep(policy), prep(value)
+                rows = self.leaf_rows() if dense else n
+                if rows > 0:
+                    policy, value = evaluator(planes[:rows])
+                    policy, value = prep(policy), prep(value)
+                else:                                   # only kept trees resuming: nothing to evaluate this round
+                    policy, value = planes[:1, 0].reshape(-1)[:400], planes[:1, 0].reshape(-1)[:4]
+                    policy, value = prep(policy), prep(value)
                 pending = self.expand_backup(ptr(policy), ptr(value))
                 rounds += 1
                 if pending > 0:

@@ -94,12 +94,14 @@ class TensorCoreLeafEvaluator:
     @torch.no_grad()
     def __call__(self, planes: torch.Tensor):
         batch = planes.shape[0]
-        key = (batch, planes.device)
-        if key not in self._bufs:
+        key = planes.device
+        if key not in self._bufs or self._bufs[key][2] < batch:      # grow-only buffers: batch sizes vary round to round
             rows = batch * PAD * PAD
             self._bufs[key] = ([torch.zeros((rows, 256), dtype=torch.bfloat16, device=planes.device) for _ in range(3)],
-                               torch.zeros((rows, 64), dtype=torch.bfloat16, device=planes.device))
-        (a, t, b), x64 = self._bufs[key]
+                               torch.zeros((rows, 64), dtype=torch.bfloat16, device=planes.device), batch)
+        (a, t, b), x64, _cap = self._bufs[key]
+        rows = batch * PAD * PAD
+        a, t, b, x64 = a[:rows], t[:rows], b[:rows], x64[:rows]
         x64.view(batch, PAD, PAD, 64)[:, :20, :20, :5] = planes.permute(0, 2, 3, 1).to(torch.bfloat16)
         conv3x3_in(x64, self.w_in, self.b_in, False, batch, out=a, lib=self.lib)      # model.input (no BN / ReLU, resnet.py:79)
         for (w1, b1), (w2, b2) in self.blocks:

@@ -24,6 +24,7 @@ struct bk_selfplay {
     BkSearchHdr* d_hdr = nullptr;
     BkPend* d_pend = nullptr;         // [n][leaves_per_round], multi-leaf mode only
     uint32_t* d_remap = nullptr;      // [n][2 * max_nodes], tree-reuse mode only
+    uint32_t* d_slot_base = nullptr;  // [n + 1], multi-leaf mode: first dense evaluator row of each game's leaves (+ total)
     bool use_vl = false;
     int num_sms = 148;
     int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
@@ -53,7 +54,7 @@ __global__ void k_sp_summary(const BkState* __restrict__ states, BkSummary* __re
 }
 
 struct BkPools {
-    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr; BkPend* pend; uint32_t* remap;
+    uint4* S; uint4* X; BkState* nodes; double* scratch; BkSearchHdr* hdr; BkPend* pend; uint32_t* remap; uint32_t* slot_base;
     uint32_t* pol_off; uint16_t* pol_tile; uint32_t* pol_visits;
 };
 
@@ -96,6 +97,36 @@ __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl
     kb_sp_begin(cfg, states, bk_tree_of(pl, cfg, g), &pl.hdr[g], g, lane);
 }
 
+// multi-leaf mode: the evaluator batch is DENSE — game g's leaves occupy rows slot_base[g] .. slot_base[g + 1) in
+// (game, slot) order, slot_base[n] = rows to evaluate — so the evaluator never works on empty slots.  One CTA, chunked scan.
+__global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 256) {
+        const int g = c0 + int(threadIdx.x);
+        uint32_t cnt = 0u;
+        if (g < n) {
+            const uint32_t k = pl.hdr[g].pend_kind;
+            cnt = k == BK_PEND_ROOT ? 1u : (k == BK_PEND_LEAF ? pl.hdr[g].pend_count : 0u);
+        }
+        uint32_t incl = cnt;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        uint32_t before = carry;
+        for (int i = 0; i < w; ++i) before += warp_tot[i];
+        if (g < n) pl.slot_base[g] = before + incl - cnt;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pl.slot_base[n] = carry;
+}
+
 // planes of every game's pending position, float32 [n][5][20][20]; counts pending games
 __global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* __restrict__ out,
                             int32_t* __restrict__ pending) {
@@ -114,6 +145,11 @@ __global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* _
         }
     }
     float* o = out + size_t(blockIdx.x) * 2000;
+    if (vl) {                                        // dense rows: nothing is written for empty slots
+        if (pend) kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], out + size_t(pl.slot_base[g] + uint32_t(j)) * 2000, threadIdx.x, blockDim.x);
+        if ((pend || resume) && threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
+        return;
+    }
     if (pend) {
         kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], o, threadIdx.x, blockDim.x);
         if (threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
@@ -152,8 +188,9 @@ k_sp_step_vl(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const floa
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
-    kb_sp_step_vl(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], pl.pend + size_t(g) * cfg.leaves_per_round, policy, value,
-                  counters, g, lane, tabs, wsm);
+    const uint32_t row0 = pl.slot_base[g];           // this game's first dense evaluator row (valid while it has leaves out)
+    kb_sp_step_vl(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], pl.pend + size_t(g) * cfg.leaves_per_round, policy + size_t(row0) * 400,
+                  value + size_t(row0) * 4, counters, g, lane, tabs, wsm);
 }
 
 __global__ void __launch_bounds__(32)
@@ -228,7 +265,7 @@ static float host_exp_f32(float x) { return float(std::exp(double(x))); }  // sa
 static BkPools pools_of(const bk_selfplay* sp) {
     BkPools p;
     p.S = sp->d_S; p.X = sp->d_X; p.nodes = sp->d_nodes; p.scratch = sp->d_scratch;
-    p.hdr = sp->d_hdr; p.pend = sp->d_pend; p.remap = sp->d_remap; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
+    p.hdr = sp->d_hdr; p.pend = sp->d_pend; p.remap = sp->d_remap; p.slot_base = sp->d_slot_base; p.pol_off = sp->d_pol_off; p.pol_tile = sp->d_pol_tile; p.pol_visits = sp->d_pol_visits;
     return p;
 }
 
@@ -353,6 +390,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_ply_off);
     cudaFree(sp->d_pend);
     cudaFree(sp->d_remap);
+    cudaFree(sp->d_slot_base);
     cudaFree(sp->d_pack_off); cudaFree(sp->d_pack_ptr); cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits);
     if (sp->ev0) cudaEventDestroy(sp->ev0);
     if (sp->ev1) cudaEventDestroy(sp->ev1);
@@ -388,6 +426,7 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
     if (vl && (!sp->d_pend || uint32_t(leaves_per_round) > sp->dcfg.leaves_per_round)) {
         cudaFree(sp->d_pend);
     cudaFree(sp->d_remap);
+    cudaFree(sp->d_slot_base);
     cudaFree(sp->d_pack_off); cudaFree(sp->d_pack_ptr); cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits);
         sp->d_pend = nullptr;
         BK_CUDA(cudaMalloc(&sp->d_pend, sizeof(BkPend) * size_t(sp->n) * size_t(leaves_per_round)));
@@ -398,6 +437,10 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
         for (BkSearchHdr& x : h) x.reused = 0u;
         BK_CUDA(cudaMemcpyAsync(sp->d_hdr, h.data(), sizeof(BkSearchHdr) * h.size(), cudaMemcpyHostToDevice, sp->env->stream));
         BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    }
+    if (vl && !sp->d_slot_base) {
+        BK_CUDA(cudaMalloc(&sp->d_slot_base, sizeof(uint32_t) * (size_t(sp->n) + 1)));
+        BK_CUDA(cudaMemsetAsync(sp->d_slot_base, 0, sizeof(uint32_t) * (size_t(sp->n) + 1), sp->env->stream));
     }
     sp->use_vl = vl;
     sp->dcfg.mode = flags;
@@ -460,13 +503,26 @@ int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending
     cudaStream_t st = sp->env->stream;
     int32_t* d_cnt = sp->env->d_i32 + 2;
     BK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t), st));
-BK_LAUNCH(k_sp_planes, sp->n * int(sp->dcfg.leaves_per_round), 256, st, sp->dcfg, pools_of(sp), sp->n,
+    if (sp->use_vl) BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n);
+    BK_LAUNCH(k_sp_planes, sp->n * int(sp->dcfg.leaves_per_round), 256, st, sp->dcfg, pools_of(sp), sp->n,
               sp->use_vl ? 1 : 0, dev_planes, d_cnt);
     BK_CUDA(cudaGetLastError());
     if (pending_out) {
         BK_CUDA(cudaMemcpyAsync(pending_out, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         BK_CUDA(cudaStreamSynchronize(st));
     }
+    return BK_OK;
+}
+
+int bk_selfplay_leaf_rows(bk_selfplay* sp, int32_t* rows_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!rows_out) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_leaf_rows: null argument");
+    if (!sp->use_vl) { *rows_out = sp->n; return BK_OK; }          // exact mode: one row per game, by game index
+    uint32_t rows = 0;
+    BK_CUDA(cudaMemcpyAsync(&rows, sp->d_slot_base + sp->n, sizeof(uint32_t), cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    *rows_out = int32_t(rows);
     return BK_OK;
 }
 

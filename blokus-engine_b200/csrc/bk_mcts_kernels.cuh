@@ -887,8 +887,8 @@ __device__ __forceinline__ void kb_sp_step_vl(const BkSearchCfg& cfg, const BkTr
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
     const uint32_t K = cfg.leaves_per_round;
-    const float* pol = policy + size_t(g) * K * 400;
-    const float* vals = value + size_t(g) * K * 4;
+    const float* pol = policy;          // the caller passes this game's first dense evaluator row
+    const float* vals = value;
     BkRegs L;
     BkBlock root;
     if (hd.pend_kind == BK_PEND_RESUME) {                // kept tree: nothing to consume, run on

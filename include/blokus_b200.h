@@ -209,6 +209,9 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies);
 int bk_selfplay_begin_ply(bk_selfplay* sp);
 int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending_out);
 int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* pending_out);
+/* Rows of the evaluator batch the last bk_selfplay_leaf_planes wrote: n_games in the exact mode (row g = game g, zero
+ * planes for games with nothing pending), the number of leaves outstanding in the multi-leaf mode (dense rows). */
+int bk_selfplay_leaf_rows(bk_selfplay* sp, int32_t* rows_out);
 int bk_selfplay_end_ply(bk_selfplay* sp);
 /* Opt-in throughput modes.  The default (flags 0, leaves_per_round 1) is the
  * reference's exact behaviour — mcts() runs sims_per_move simulations one at a time from a fresh tree
@@ -217,9 +220,11 @@ int bk_selfplay_end_ply(bk_selfplay* sp);
  *                              [(tile, sims_per_move visits)] = [(tile, 1.0)] and its action are what the search
  *                              would return anyway (simulation.rs:213-229), so the training tuple is unchanged.
  *   leaves_per_round K > 1   : (external-evaluator protocol) up to K simulations per game are in flight per
- *                              round, separated by virtual loss; leaf_planes / expand_backup then work on
- *                              [n_games][K] slots: planes [n*K][5][20][20], policy [n*K][400], value [n*K][4]
- *                              (slot j of game g at index g*K + j; unused slots are zero planes and ignored).
+ *                              round, separated by virtual loss.  The evaluator batch is then DENSE: the leaves of
+ *                              all games are packed in (game, slot) order into the first R rows of planes
+ *                              [<= n*K][5][20][20] (R from bk_selfplay_leaf_rows after bk_selfplay_leaf_planes), and
+ *                              expand_backup reads policy [R][400] / value [R][4] in the same order — the evaluator
+ *                              never works on empty slots.
  *                              With K == 1 results equal the exact mode bit for bit (BK_MODE_FORCE_MULTI_LEAF
  *                              runs that code path with K == 1, for tests).
  *   BK_MODE_TREE_REUSE       : after a ply's action is played, the subtree below the chosen root child is

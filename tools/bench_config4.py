@@ -38,9 +38,11 @@ sp.leaf_planes(planes.data_ptr(), want_count=False)
 t_eval = t_tree = 0.0
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 evals = 0
+dense = a.leaves > 1
 for r in range(a.warmup + a.rounds):
+    rows = sp.leaf_rows() if dense else a.games       # multi-leaf mode: the evaluator batch is dense (no empty slots)
     e0.record()
-    policy, value = ev(planes)
+    policy, value = ev(planes[:rows])
     policy, value = policy.contiguous(), value.contiguous()
     e1.record()
     sp.expand_backup(policy.data_ptr(), value.data_ptr(), want_count=False)
@@ -52,7 +54,7 @@ for r in range(a.warmup + a.rounds):
     if r >= a.warmup:
         t_eval += e0.elapsed_time(e1)
         t_tree += e1.elapsed_time(e2)
-        evals += a.games * a.leaves
+        evals += rows
 sims = sp.counters()["sims"] - sims0     # simulations actually completed (slots left empty by collisions do not count)
 flops_per_leaf = 2 * 400 * (5 * 9 * a.width + 2 * a.blocks * a.width * a.width * 9 + 2 * a.width) + 2 * 400 * 4
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
