@@ -187,8 +187,10 @@ public:
     // training_game() for every client with the fixed-prior stub evaluator, on the device (max_plies < 0: to the end)
     void run_stub(int max_plies = -1) { check(bk_selfplay_run_stub(sp_, max_plies)); }
     // training_game() with a caller-supplied evaluator working on DEVICE memory:
-    //   eval(planes[n*K][5][20][20] f32) must fill policy[n*K][400] (mover frame) and value[n*K][4] (relative seats)
-    // — the contract of the reference's inference server (model/training.py:43-67) on one contiguous batch.
+    //   eval(planes, policy, value, rows): planes[rows][5][20][20] f32 in; fill policy[rows][400] (mover frame) and
+    //   value[rows][4] (relative seats) — the contract of the reference's inference server (model/training.py:43-67) on
+    //   one contiguous batch.  rows = n games in the exact mode (row g = game g), the number of leaves outstanding in
+    //   the multi-leaf mode (dense rows, at most n * leaves_per_round; the buffers must hold that many).
     template <class Eval>
     void run_evaluator(Eval&& eval, float* dev_planes, float* dev_policy, float* dev_value, int max_plies = -1) {
         int32_t live = 0;
@@ -199,7 +201,9 @@ public:
             int32_t pending = 0;
             check(bk_selfplay_leaf_planes(sp_, dev_planes, &pending));
             while (pending > 0) {
-                eval(dev_planes, dev_policy, dev_value);
+                int32_t rows = 0;
+                check(bk_selfplay_leaf_rows(sp_, &rows));
+                if (rows > 0) eval(dev_planes, dev_policy, dev_value, int(rows));
                 check(bk_selfplay_expand_backup(sp_, dev_policy, dev_value, &pending));
                 if (pending > 0) check(bk_selfplay_leaf_planes(sp_, dev_planes, nullptr));
             }
