@@ -145,6 +145,23 @@ def mcts_measure(local_rank: int, rank: int, plies: int):
     return out
 
 
+def mcts_large_batch_measure(local_rank: int, rank: int, games: int = 8192, plies: int = 8):
+    """BASELINE.json configs[4]'s per-GPU shape (8192 games, 800 sims/move, stub evaluator): the throughput regime of the
+    same kernel (20 resident games per SM) on a prefix of the games.  Never fails the bench: returns None on any error."""
+    try:
+        from blokus_self_play import SelfPlay, Config
+        sp = SelfPlay(games, Config(**MCTS_CFG), first_game_id=rank * games, device=local_rank, max_children_per_game=24576)
+        sp.run_stub(1)
+        sp.reset()
+        c0 = sp.counters()
+        ms = sp.run_stub(plies)
+        c1 = sp.counters()
+        sp.close()
+        return {"games_per_gpu": games, "plies": plies, "sims": c1["sims"] - c0["sims"], "kernel_ms": ms}
+    except Exception as e:                      # pragma: no cover - informational block only
+        return {"error": str(e)[:200]}
+
+
 def leaf_eval_measure(local_rank: int, rounds: int = 10, warmup: int = 3) -> dict:
     """BASELINE.json configs[3] building block: one evaluator round = ResNet(20,256) forward on 1024 leaves.
     Hand-written tcgen05 trunk (bk_conv3x3_bf16) and, beside it, the PyTorch/cuDNN bf16 path."""
@@ -352,6 +369,7 @@ def main() -> int:
 
     # ---- secondary metric: MCTS sims/s (configs[2]) -------------------------------------------------
     mcts = None
+    mcts_big = None
     leaf = None
     if not args.no_mcts:
         batch.close()
@@ -360,6 +378,8 @@ def main() -> int:
         torch.cuda.empty_cache()
         barrier()
         mcts = mcts_measure(local_rank, rank, args.mcts_plies)
+        barrier()
+        mcts_big = mcts_large_batch_measure(local_rank, rank) if rank == 0 else None
         barrier()
         leaf = leaf_eval_measure(local_rank) if rank == 0 else None
     clocks = sampler.stop()     # sampled over every timed region: device-resident steps, e2e steps, MCTS, leaf evaluation
@@ -435,6 +455,15 @@ def main() -> int:
                                  "frac": mcts_lane_ops / world / (mcts_ms * 1e-3) / int_peak},
                 "child_entries_created": mcts_entries,
             }
+        if mcts_big and "error" not in mcts_big:
+            line["gpu_launches"] += 1
+            line["extra"]["mcts_large_batch"] = {
+                "metric": "mcts_sims_per_sec_fixed_priors", "value": mcts_big["sims"] / (mcts_big["kernel_ms"] * 1e-3), "unit": "sims/s",
+                "config": f"configs[4] per-GPU shape on rank 0: {mcts_big['games_per_gpu']} games, 800 sims/move, stub evaluator, "
+                          f"first {mcts_big['plies']} plies (k_selfplay_stub<20>: 20 resident games per SM)",
+                "sims": mcts_big["sims"], "kernel_ms": mcts_big["kernel_ms"]}
+        elif mcts_big:
+            line["extra"]["mcts_large_batch"] = mcts_big
         if leaf:
             flops = 18883996800.0 * MCTS_GAMES
             line["gpu_launches"] += 41 * 10          # 41 hand-written convolutions per round, 10 timed rounds
