@@ -88,3 +88,33 @@ def test_emu_packed_results_equal_per_game_records(emu_lib, orc):
             a, b = ply_ptr[ply_off[g] + k], ply_ptr[ply_off[g] + k + 1]
             assert np.array_equal(tiles[a:b], t) and np.array_equal(visits[a:b], v)
     sp.close()
+
+
+def test_emu_dense_rows_across_scan_chunks(emu_lib, orc):
+    """The multi-leaf mode's slot scan (one CTA, 256 games per chunk) on more games than one chunk: dense rows must
+    line up with the games (a wrong carry would hand game g another game's policy).  All games start from the same
+    position and the root noise is off, so with a position-dependent policy every game must end the ply with the SAME
+    root priors, children and visit counts."""
+    import numpy as np
+    from blokus_self_play import SelfPlay, Config
+    n = 262
+    cfg = Config(sims_per_move=3, sample_moves=0, c_base=19652, c_init=1.25, dirichlet_alpha=0.3, exploration_fraction=0.0, seed=5)
+    calls = []
+
+    def ev(planes):
+        pl = np.asarray(planes)
+        calls.append(pl.shape[0])
+        ramp = (np.arange(400, dtype=np.float32) % 7 + 1.0) / 7.0
+        own = pl[:, 0].reshape(-1, 400).sum(axis=1, keepdims=True)          # depends on the position, not only on the legal set
+        return (pl[:, 4].reshape(-1, 400) * ramp * (1.0 + 0.1 * own)).astype(np.float32), \
+            np.tile(np.array([0.4, 0.3, 0.2, 0.1], np.float32), (pl.shape[0], 1))
+    a = SelfPlay(n, cfg, lib=emu_lib)
+    a.set_mode(0, 2)
+    a.run_evaluator(ev, max_plies=1, xp="numpy")
+    assert calls[0] == n and max(calls) <= 2 * n            # the root round is one row per game; later rounds are dense
+    roots = a.last_root()
+    for g in (1, 255, 256, 257, n - 1):
+        for key in ("tile", "visits", "prior", "value_sum"):
+            assert np.array_equal(roots[0][key], roots[g][key]), (g, key)
+    assert int(roots[0]["visits"].sum()) == 3
+    a.close()

@@ -202,3 +202,27 @@ def test_gpu_results_packed_equal_per_game_abi(cuda_lib, orc):
         for (t1, v1), (t2, v2) in zip(ga, gb):
             assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
     sp.close()
+
+
+def test_gpu_dense_rows_many_games(cuda_lib, orc):
+    """Multi-leaf mode with more games than one chunk of the slot scan (600 games, 4 leaves per round): with the root noise
+    off and greedy actions every game is the same game, so a misplaced evaluator row would break the equality."""
+    import torch
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(**dict(CONFIG3, sims_per_move=32, sample_moves=0, exploration_fraction=0.0))
+    ramp = ((torch.arange(400, device="cuda") % 7 + 1.0) / 7.0).float()
+
+    def ev(planes):
+        n = planes.shape[0]
+        own = planes[:, 0].reshape(n, 400).sum(dim=1, keepdim=True)
+        return planes[:, 4].reshape(n, 400) * ramp * (1.0 + 0.1 * own), torch.tensor([0.4, 0.3, 0.2, 0.1], device=planes.device).repeat(n, 1)
+    sp = SelfPlay(600, cfg, lib=cuda_lib)
+    sp.set_mode(0, 4)
+    sp.run_evaluator(ev, max_plies=5)
+    hist = sp.env.history()
+    assert all(h == hist[0] for h in hist)
+    recs = sp.policy_records()
+    for g in (1, 255, 256, 257, 511, 512, 599):
+        for (t1, v1), (t2, v2) in zip(recs[0], recs[g]):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    sp.close()
