@@ -34,6 +34,41 @@ def _to_bk_config(config) -> BkConfig:
                     float(config.dirichlet_alpha), float(config.exploration_fraction), int(getattr(config, "seed", 0)))
 
 
+class TorchBuffers:
+    """Where the evaluator batches live: CUDA tensors on the handle's device, on torch's current stream.  Any object
+    with the same four methods can stand in (a caller that owns device memory by other means)."""
+
+    def __init__(self, device: int):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+
+    def stream(self) -> int:
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def zeros(self, shape):
+        return self.torch.zeros(shape, dtype=self.torch.float32, device=self.dev)
+
+    def empty(self, shape):
+        t = self.torch.empty(shape, dtype=self.torch.float32, device=self.dev)
+        self.torch.cuda.synchronize(self.dev)
+        return t
+
+    def f32(self, t):
+        return t.to(dtype=self.torch.float32).contiguous()
+
+    @staticmethod
+    def ptr(t) -> int:
+        return t.data_ptr()
+
+    @staticmethod
+    def to_host(t) -> np.ndarray:
+        return t.detach().cpu().numpy()
+
+    def from_host(self, a: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev)
+
+
 class SelfPlay:
     """n self-play clients (bk_selfplay).  Game g has global id first_game_id + g."""
 
@@ -110,45 +145,37 @@ class SelfPlay:
     def end_ply(self) -> None:
         self.lib.check(self.lib.bk_selfplay_end_ply(self._h))
 
-    def run_evaluator(self, evaluator: Callable, max_plies: int = -1, xp: str = "torch") -> dict:
+    def run_evaluator(self, evaluator: Callable, max_plies: int = -1, buffers=None) -> dict:
         """training_game() for every client with a caller-supplied evaluator.
 
         evaluator(planes[R,5,20,20] float32) -> (policy[R,400] float32 in the mover's frame, value[R,4] float32
         in relative-seat order), exactly the contract of the reference's inference server
-        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous batch: R = n games in the exact mode
-        (row g = game g), R = the leaves outstanding in the multi-leaf mode (dense rows, at most n x leaves_per_round).
-        xp="torch": CUDA tensors on this handle's device; xp="numpy": host arrays, valid only with the tests'
-        CPU-emulator build of the library (where "device" memory is host memory)."""
+        (model/training.py:43-67, model/resnet.py:69-94), but on ONE contiguous device batch.  Rows are DENSE in
+        every mode: only positions that wait for an answer are written and evaluated (R = the live games with a
+        leaf out in the exact mode, the leaves outstanding in the multi-leaf mode), in (game, slot) order.
+        `buffers` owns the batch memory (default: CUDA tensors on this handle's device, TorchBuffers)."""
         n = self.n * self.leaves_per_round      # capacity of the evaluator batch
-        dense = self.leaves_per_round > 1 or bool(self.mode & _lib.MODE_FORCE_MULTI_LEAF)
-        if xp == "torch":
-            import torch
-            dev = torch.device("cuda", self.env.device)
-            planes = torch.zeros((n, 5, 20, 20), dtype=torch.float32, device=dev)
-            self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-            ptr = lambda t: t.data_ptr()
-            prep = lambda t: t.to(dtype=torch.float32).contiguous()
-        else:
-            planes = np.zeros((n, 5, 20, 20), dtype=np.float32)
-            ptr = lambda a: a.ctypes.data
-            prep = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        buf = buffers or TorchBuffers(self.env.device)
+        planes = buf.zeros((n, 5, 20, 20))
+        if hasattr(buf, "stream"):
+            self.set_stream(buf.stream())
         rounds = 0
         plies = 0
         while (max_plies < 0 or plies < max_plies) and self.live_games() > 0:
             self.begin_ply()
-            pending = self.leaf_planes(ptr(planes))
+            pending = self.leaf_planes(buf.ptr(planes))
             while pending > 0:
-                rows = self.leaf_rows() if dense else n
+                rows = self.leaf_rows()
                 if rows > 0:
                     policy, value = evaluator(planes[:rows])
-                    policy, value = prep(policy), prep(value)
+                    policy, value = buf.f32(policy), buf.f32(value)
                 else:                                   # only kept trees resuming: nothing to evaluate this round
                     policy, value = planes[:1, 0].reshape(-1)[:400], planes[:1, 0].reshape(-1)[:4]
-                    policy, value = prep(policy), prep(value)
-                pending = self.expand_backup(ptr(policy), ptr(value))
+                    policy, value = buf.f32(policy), buf.f32(value)
+                pending = self.expand_backup(buf.ptr(policy), buf.ptr(value))
                 rounds += 1
                 if pending > 0:
-                    self.leaf_planes(ptr(planes), want_count=False)
+                    self.leaf_planes(buf.ptr(planes), want_count=False)
             self.end_ply()
             plies += 1
         return {"plies": plies, "rounds": rounds}
@@ -219,28 +246,16 @@ class SelfPlay:
         return [{"tile": tile[g, : cnt[g]].copy(), "visits": vis[g, : cnt[g]].copy(), "value_sum": w[g, : cnt[g]].copy(),
                  "prior": p[g, : cnt[g]].copy()} for g in range(self.n)]
 
-    def training_tensors(self, xp: str = "torch"):
+    def training_tensors(self, buffers=None):
         """`save()` of model/training.py:70-119 on the device: (states[P,5,20,20], policies[P,400], values[P,4],
-        ply_offsets[n+1]) over all searched plies P, game-major.  xp="torch": CUDA tensors; xp="numpy": host
-        arrays (CPU-emulator build only)."""
+        ply_offsets[n+1]) over all searched plies P, game-major, in `buffers`' memory (default: CUDA tensors)."""
         total = C.c_int64(0)
         offs = np.zeros(self.n + 1, dtype=np.int64)
         self.lib.check(self.lib.bk_selfplay_training_sizes(self._h, C.byref(total), _ptr(offs)))
         P = max(int(total.value), 1)
-        if xp == "torch":
-            import torch
-            dev = torch.device("cuda", self.env.device)
-            st = torch.empty((P, 5, 20, 20), dtype=torch.float32, device=dev)
-            po = torch.empty((P, 400), dtype=torch.float32, device=dev)
-            va = torch.empty((P, 4), dtype=torch.float32, device=dev)
-            torch.cuda.synchronize(dev)
-            ptrs = [t.data_ptr() for t in (st, po, va)]
-        else:
-            st = np.empty((P, 5, 20, 20), dtype=np.float32)
-            po = np.empty((P, 400), dtype=np.float32)
-            va = np.empty((P, 4), dtype=np.float32)
-            ptrs = [a.ctypes.data for a in (st, po, va)]
-        self.lib.check(self.lib.bk_selfplay_training_tensors(self._h, *[C.c_void_p(p) for p in ptrs]))
+        buf = buffers or TorchBuffers(self.env.device)
+        st, po, va = buf.empty((P, 5, 20, 20)), buf.empty((P, 400)), buf.empty((P, 4))
+        self.lib.check(self.lib.bk_selfplay_training_tensors(self._h, *[C.c_void_p(buf.ptr(t)) for t in (st, po, va)]))
         n = int(total.value)
         return st[:n], po[:n], va[:n], offs
 
@@ -287,7 +302,7 @@ def host_evaluator(fn: Callable):
     return wrapped
 
 
-def play_training_game(id: int, config, inference_queue, pipe, device: int = 0, lib: Optional[Lib] = None):
+def play_training_game(id: int, config, inference_queue, pipe, device: int = 0, lib: Optional[Lib] = None, buffers=None):
     """Drop-in for the reference's `play_training_game(id, config, inference_queue, pipe)`
     (self_play/src/lib.rs:9-32): one game, every leaf sent to the Python inference server with the
     reference's own protocol — `inference_queue.put((id, planes))` with planes as nested bool lists
@@ -295,15 +310,16 @@ def play_training_game(id: int, config, inference_queue, pipe, device: int = 0, 
     (history, policies, values).  This keeps `model/training.py` running unmodified; the batched
     `SelfPlay.run_evaluator` is the fast path."""
     sp = SelfPlay(1, config, first_game_id=int(id), device=device, lib=lib)
+    buf = buffers or TorchBuffers(device)
 
-    def ev(planes_np):
-        inference_queue.put((id, planes_np[0].astype(bool).tolist()))
+    def ev(planes):
+        inference_queue.put((id, buf.to_host(planes)[0].astype(bool).tolist()))
         policy, value = pipe.recv()
-        return np.asarray(policy, dtype=np.float32)[None, :], np.asarray(value, dtype=np.float32)[None, :]
+        return (buf.from_host(np.asarray(policy, dtype=np.float32)[None, :]),
+                buf.from_host(np.asarray(value, dtype=np.float32)[None, :]))
 
     try:
-        emulated = "emu" in sp.lib.path
-        sp.run_evaluator(ev if emulated else host_evaluator(ev), -1, xp="numpy" if emulated else "torch")
+        sp.run_evaluator(ev, -1, buffers=buf)
         return sp.game_data()[0]
     finally:
         sp.close()

@@ -22,9 +22,10 @@ struct bk_selfplay {
     BkState* d_nodes = nullptr;
     double* d_scratch = nullptr;
     BkSearchHdr* d_hdr = nullptr;
-    BkPend* d_pend = nullptr;         // [n][leaves_per_round], multi-leaf mode only
+    BkPend* d_pend = nullptr;         // [n][pend_cap], multi-leaf mode only
+    uint32_t pend_cap = 0;            // leaves per round d_pend was allocated for
     uint32_t* d_remap = nullptr;      // [n][2 * max_nodes], tree-reuse mode only
-    uint32_t* d_slot_base = nullptr;  // [n + 1], multi-leaf mode: first dense evaluator row of each game's leaves (+ total)
+    uint32_t* d_slot_base = nullptr;  // [n + 1]: first dense evaluator row of each game's outstanding positions (+ total)
     bool use_vl = false;
     int num_sms = 148;
     int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
@@ -97,9 +98,10 @@ __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl
     kb_sp_begin(cfg, states, bk_tree_of(pl, cfg, g), &pl.hdr[g], g, lane);
 }
 
-// multi-leaf mode: the evaluator batch is DENSE — game g's leaves occupy rows slot_base[g] .. slot_base[g + 1) in
-// (game, slot) order, slot_base[n] = rows to evaluate — so the evaluator never works on empty slots.  One CTA, chunked scan.
-__global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n) {
+// The evaluator batch is DENSE in every mode — game g's outstanding positions (one in the exact mode, up to
+// leaves_per_round in the multi-leaf mode) occupy rows slot_base[g] .. slot_base[g + 1) in (game, slot) order,
+// slot_base[n] = rows to evaluate — so the evaluator never works on finished games or empty slots.  One CTA, chunked scan.
+__global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n, int vl) {
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0u;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n) {
         uint32_t cnt = 0u;
         if (g < n) {
             const uint32_t k = pl.hdr[g].pend_kind;
-            cnt = k == BK_PEND_ROOT ? 1u : (k == BK_PEND_LEAF ? pl.hdr[g].pend_count : 0u);
+            cnt = k == BK_PEND_ROOT ? 1u : (k == BK_PEND_LEAF ? (vl ? pl.hdr[g].pend_count : 1u) : 0u);
         }
         uint32_t incl = cnt;
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -144,19 +146,9 @@ __global__ void k_sp_planes(BkSearchCfg cfg, BkPools pl, int n, int vl, float* _
             if (pend) slot = pl.pend[size_t(g) * cfg.leaves_per_round + j].slot;
         }
     }
-    float* o = out + size_t(blockIdx.x) * 2000;
-    if (vl) {                                        // dense rows: nothing is written for empty slots
-        if (pend) kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], out + size_t(pl.slot_base[g] + uint32_t(j)) * 2000, threadIdx.x, blockDim.x);
-        if ((pend || resume) && threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
-        return;
-    }
-    if (pend) {
-        kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], o, threadIdx.x, blockDim.x);
-        if (threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
-    } else {
-        for (int e = threadIdx.x; e < 2000; e += blockDim.x) o[e] = 0.0f;
-        if (resume && threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
-    }
+    // dense rows: nothing is written for games / slots without a position waiting
+    if (pend) kb_planes<float>(&bk_tree_of(pl, cfg, g).nodes[slot], out + size_t(pl.slot_base[g] + uint32_t(j)) * 2000, threadIdx.x, blockDim.x);
+    if ((pend || resume) && threadIdx.x == 0 && j == 0) atomicAdd(pending, 1);
 }
 
 __global__ void k_sp_count(BkPools pl, int n, int32_t* __restrict__ counts) {
@@ -176,7 +168,9 @@ k_sp_step(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* 
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
-    kb_sp_step(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], policy, value, counters, g, lane, tabs, wsm);
+    const uint32_t row = pl.slot_base[g];            // this game's dense evaluator row (valid while its position is out)
+    kb_sp_step(cfg, bk_tree_of(pl, cfg, g), &pl.hdr[g], policy + size_t(row) * 400, value + size_t(row) * 4, counters, g, lane,
+               tabs, wsm);
 }
 
 __global__ void __launch_bounds__(32)
@@ -351,6 +345,8 @@ static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_
     BK_CUDA(cudaMalloc(&sp->d_pol_visits, sizeof(uint32_t) * size_t(d.policy_cap) * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 8));
     BK_CUDA(cudaMalloc(&sp->d_stage, size_t(n_games) * 400 * 16));
+    BK_CUDA(cudaMalloc(&sp->d_slot_base, sizeof(uint32_t) * (size_t(n_games) + 1)));
+    BK_CUDA(cudaMemsetAsync(sp->d_slot_base, 0, sizeof(uint32_t) * (size_t(n_games) + 1), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned long long) * 8, sp->env->stream));
@@ -423,13 +419,12 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
     for (const BkSearchHdr& x : h)
         if (x.pend_kind != BK_PEND_NONE) return bk_fail(BK_ERR_STATE, "bk_selfplay_set_mode: a ply is in progress");
     const bool vl = leaves_per_round > 1 || (flags & BK_MODE_FORCE_MULTI_LEAF);
-    if (vl && (!sp->d_pend || uint32_t(leaves_per_round) > sp->dcfg.leaves_per_round)) {
+    if (vl && uint32_t(leaves_per_round) > sp->pend_cap) {       // grow-only; no other buffer depends on K
         cudaFree(sp->d_pend);
-    cudaFree(sp->d_remap);
-    cudaFree(sp->d_slot_base);
-    cudaFree(sp->d_pack_off); cudaFree(sp->d_pack_ptr); cudaFree(sp->d_pack_tile); cudaFree(sp->d_pack_visits);
         sp->d_pend = nullptr;
+        sp->pend_cap = 0u;
         BK_CUDA(cudaMalloc(&sp->d_pend, sizeof(BkPend) * size_t(sp->n) * size_t(leaves_per_round)));
+        sp->pend_cap = uint32_t(leaves_per_round);
     }
     if ((flags & BK_MODE_TREE_REUSE) && !sp->d_remap)
         BK_CUDA(cudaMalloc(&sp->d_remap, sizeof(uint32_t) * 2 * size_t(sp->dcfg.max_nodes) * size_t(sp->n)));
@@ -437,10 +432,6 @@ int bk_selfplay_set_mode(bk_selfplay* sp, uint32_t flags, int leaves_per_round) 
         for (BkSearchHdr& x : h) x.reused = 0u;
         BK_CUDA(cudaMemcpyAsync(sp->d_hdr, h.data(), sizeof(BkSearchHdr) * h.size(), cudaMemcpyHostToDevice, sp->env->stream));
         BK_CUDA(cudaStreamSynchronize(sp->env->stream));
-    }
-    if (vl && !sp->d_slot_base) {
-        BK_CUDA(cudaMalloc(&sp->d_slot_base, sizeof(uint32_t) * (size_t(sp->n) + 1)));
-        BK_CUDA(cudaMemsetAsync(sp->d_slot_base, 0, sizeof(uint32_t) * (size_t(sp->n) + 1), sp->env->stream));
     }
     sp->use_vl = vl;
     sp->dcfg.mode = flags;
@@ -503,7 +494,7 @@ int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending
     cudaStream_t st = sp->env->stream;
     int32_t* d_cnt = sp->env->d_i32 + 2;
     BK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t), st));
-    if (sp->use_vl) BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n);
+    BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n, sp->use_vl ? 1 : 0);
     BK_LAUNCH(k_sp_planes, sp->n * int(sp->dcfg.leaves_per_round), 256, st, sp->dcfg, pools_of(sp), sp->n,
               sp->use_vl ? 1 : 0, dev_planes, d_cnt);
     BK_CUDA(cudaGetLastError());
@@ -518,7 +509,6 @@ int bk_selfplay_leaf_rows(bk_selfplay* sp, int32_t* rows_out) {
     int rc = sp_use(sp);
     if (rc) return rc;
     if (!rows_out) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_leaf_rows: null argument");
-    if (!sp->use_vl) { *rows_out = sp->n; return BK_OK; }          // exact mode: one row per game, by game index
     uint32_t rows = 0;
     BK_CUDA(cudaMemcpyAsync(&rows, sp->d_slot_base + sp->n, sizeof(uint32_t), cudaMemcpyDeviceToHost, sp->env->stream));
     BK_CUDA(cudaStreamSynchronize(sp->env->stream));

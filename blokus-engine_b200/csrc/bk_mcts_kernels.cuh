@@ -733,7 +733,7 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
-    const float* pol = policy + size_t(g) * 400;
+    const float* pol = policy;                           // the caller passes this game's dense evaluator row
     BkRegs L;
     BkBlock root;
     if (hd.pend_kind == BK_PEND_RESUME) {                // kept tree: nothing to consume, run on
@@ -752,7 +752,7 @@ __device__ __forceinline__ void kb_sp_step(const BkSearchCfg& cfg, const BkTree&
         bk_tree_link(tr, hd.pend_entry, int(hd.pend_tile), id, cur, blk, lane);
         float val[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) val[i] = value[size_t(g) * 4 + ((i + 4 - cur) & 3)];   // value.rotate_right(cur)
+        for (int i = 0; i < 4; ++i) val[i] = value[(i + 4 - cur) & 3];                     // value.rotate_right(cur)
         if (lane == 0) sm.path_tp[hd.pend_depth - 1] = uint8_t(cur);
         __syncwarp();
         bk_tree_backup(tr, int(hd.pend_depth), val, lane, sm);
@@ -807,6 +807,13 @@ __device__ __forceinline__ void kb_sp_end(const BkSearchCfg& cfg, BkState* __res
     BkSearchHdr hd;
     bk_hdr_load(hdr_g, hd, tr, lane, sm);
     if (hd.pend_kind != BK_PEND_DONE) return;
+    if (hd.err != 0u) {
+        // A search that stopped on an error (no selectable root child, a full pool, a path over the cap) has no
+        // trustworthy root block: nothing is recorded or played; the host reports hd.err (sp_check_errors).
+        __syncwarp();
+        if (lane == 0) hdr_g->pend_kind = BK_PEND_NONE;
+        return;
+    }
     BkRegs G;
     bk_load(&states[g], lane, G);
     BkCounters gctr = {0u, 0u};

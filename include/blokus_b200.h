@@ -194,12 +194,15 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies);
  * simulation.rs:50-57 by one contiguous device batch).  Per ply:
  *   bk_selfplay_begin_ply     : start mcts() for every live game; its root position becomes the pending leaf.
  *   loop until no game is pending:
- *     bk_selfplay_leaf_planes   : dev_planes[n_games][5][20][20] float32 = get_board_state() of each game's
- *                                 pending position (zeros for games with none); pending_out (host, may be NULL)
- *                                 = number of games with a pending position.
- *     (caller runs its evaluator on the device batch)
- *     bk_selfplay_expand_backup : consume dev_policy[n_games][400] (mover frame) and dev_value[n_games][4]
- *                                 (relative seat): expand the pending position (children for legal tiles with
+ *     bk_selfplay_leaf_planes   : dev_planes[R][5][20][20] float32 = get_board_state() of every pending
+ *                                 position, DENSE: the R positions waiting for an answer are packed in game order
+ *                                 into the first R rows of a buffer of capacity n_games (x leaves_per_round) rows —
+ *                                 finished games and games whose ply is done cost the evaluator nothing.
+ *                                 R = bk_selfplay_leaf_rows.  pending_out (host, may be NULL) = number of games
+ *                                 that need the next expand_backup call.
+ *     (caller runs its evaluator on the first R rows of the device batch)
+ *     bk_selfplay_expand_backup : consume dev_policy[R][400] (mover frame) and dev_value[R][4]
+ *                                 (relative seat), same row order: expand the pending position (children for legal tiles with
  *                                 policy > 0, priors exp(p)/sum), back the value up, then run further
  *                                 simulations until each game's next NON-terminal leaf is pending (terminal
  *                                 leaves are backed up on the device) or its sims_per_move are done.
@@ -209,8 +212,8 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies);
 int bk_selfplay_begin_ply(bk_selfplay* sp);
 int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending_out);
 int bk_selfplay_expand_backup(bk_selfplay* sp, const float* dev_policy, const float* dev_value, int32_t* pending_out);
-/* Rows of the evaluator batch the last bk_selfplay_leaf_planes wrote: n_games in the exact mode (row g = game g, zero
- * planes for games with nothing pending), the number of leaves outstanding in the multi-leaf mode (dense rows). */
+/* Rows R of the evaluator batch the last bk_selfplay_leaf_planes wrote = positions waiting for an answer (at most
+ * n_games in the exact mode, n_games x leaves_per_round in the multi-leaf mode). */
 int bk_selfplay_leaf_rows(bk_selfplay* sp, int32_t* rows_out);
 int bk_selfplay_end_ply(bk_selfplay* sp);
 /* Opt-in throughput modes.  The default (flags 0, leaves_per_round 1) is the

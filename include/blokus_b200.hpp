@@ -189,8 +189,8 @@ public:
     // training_game() with a caller-supplied evaluator working on DEVICE memory:
     //   eval(planes, policy, value, rows): planes[rows][5][20][20] f32 in; fill policy[rows][400] (mover frame) and
     //   value[rows][4] (relative seats) — the contract of the reference's inference server (model/training.py:43-67) on
-    //   one contiguous batch.  rows = n games in the exact mode (row g = game g), the number of leaves outstanding in
-    //   the multi-leaf mode (dense rows, at most n * leaves_per_round; the buffers must hold that many).
+    //   one contiguous batch.  rows = the positions waiting for an answer, dense in game order (at most n in the
+    //   exact mode, n * leaves_per_round in the multi-leaf mode; the buffers must hold that many).
     template <class Eval>
     void run_evaluator(Eval&& eval, float* dev_planes, float* dev_policy, float* dev_value, int max_plies = -1) {
         int32_t live = 0;

@@ -5,6 +5,37 @@ import numpy as np
 from blokus_self_play import GameBatch, PLAYOUT_HASH, PLAYOUT_MIN_TILE, PLAYOUT_MAX_TILE, BkError
 
 
+class HostBuffers:
+    """Evaluator batches in HOST memory: only meaningful with the tests' CPU warp-emulator build of the kernel sources
+    (tests/warp_emu), where "device" pointers are host pointers.  The product's default is TorchBuffers (CUDA)."""
+
+    @staticmethod
+    def zeros(shape):
+        return np.zeros(shape, dtype=np.float32)
+
+    empty = zeros
+
+    @staticmethod
+    def f32(a):
+        return np.ascontiguousarray(a, dtype=np.float32)
+
+    @staticmethod
+    def ptr(a):
+        return a.ctypes.data
+
+    @staticmethod
+    def to_host(a):
+        return np.asarray(a)
+
+    @staticmethod
+    def from_host(a):
+        return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _buffers(xp):
+    return HostBuffers() if xp == "numpy" else None
+
+
 def oracle_mask(tiles):
     m = np.zeros(400, dtype=np.uint8)
     m[list(tiles)] = 1
@@ -275,7 +306,7 @@ def check_selfplay_evaluator(lib, orc, n_games, cfg_kwargs, first_game_id=0, max
     ocfg = orc.make_config(cfg.sims_per_move, cfg.sample_moves, float(cfg.c_base), float(cfg.c_init),
                            float(cfg.dirichlet_alpha), float(cfg.exploration_fraction), cfg.seed)
     sp = SelfPlay(n_games, cfg, first_game_id=first_game_id, lib=lib)
-    info = sp.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, xp=xp)
+    info = sp.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, buffers=_buffers(xp))
     recs = sp.policy_records()
     hist = sp.env.history()
     roots = sp.last_root()
@@ -313,13 +344,13 @@ class FakeQueue:
         return self.answers.pop(0)
 
 
-def check_play_training_game(lib, orc, cfg_kwargs, game_id=7):
+def check_play_training_game(lib, orc, cfg_kwargs, game_id=7, xp="torch"):
     """The reference's own entry point signature, play_training_game(id, config, inference_queue, pipe)."""
     from blokus_self_play import play_training_game, Config
     _, single = fixed_network(1)
     q = FakeQueue(single)
     cfg = Config(**cfg_kwargs)
-    history, policies, values = play_training_game(game_id, cfg, q, q, lib=lib)
+    history, policies, values = play_training_game(game_id, cfg, q, q, lib=lib, buffers=_buffers(xp))
     ocfg = orc.make_config(cfg.sims_per_move, cfg.sample_moves, float(cfg.c_base), float(cfg.c_init),
                            float(cfg.dirichlet_alpha), float(cfg.exploration_fraction), cfg.seed)
     ref = orc.selfplay_game(ocfg, game_id, evaluator=single)
@@ -343,7 +374,7 @@ def check_training_tensors(lib, orc, n_games, cfg_kwargs, max_plies, xp):
     from oracle.save_oracle import save_arrays
     sp = SelfPlay(n_games, Config(**cfg_kwargs), first_game_id=2, lib=lib)
     sp.run_stub(max_plies)
-    st, po, va, offs = sp.training_tensors(xp=xp)
+    st, po, va, offs = sp.training_tensors(buffers=_buffers(xp))
     if xp == "torch":
         st, po, va = st.cpu().numpy(), po.cpu().numpy(), va.cpu().numpy()
     data = sp.game_data()
@@ -411,11 +442,11 @@ def check_throughput_modes(lib, n_games, cfg_kwargs, max_plies, xp, leaves=4, ne
     cfg = Config(**cfg_kwargs)
 
     exact = SelfPlay(n_games, cfg, lib=lib)
-    info_exact = exact.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    info_exact = exact.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
 
     one = SelfPlay(n_games, cfg, lib=lib)
     one.set_mode(MODE_FORCE_MULTI_LEAF, 1)
-    one.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    one.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
     assert one.env.history() == exact.env.history()
     _records_equal(one, exact)
     for x, y in zip(one.last_root(), exact.last_root()):
@@ -425,7 +456,7 @@ def check_throughput_modes(lib, n_games, cfg_kwargs, max_plies, xp, leaves=4, ne
 
     skip = SelfPlay(n_games, cfg, lib=lib)
     skip.set_mode(MODE_SKIP_FORCED, 1)
-    info_skip = skip.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    info_skip = skip.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
     assert skip.env.history() == exact.env.history()
     _records_equal(skip, exact)
     assert skip.counters()["sims"] <= exact.counters()["sims"]
@@ -433,7 +464,7 @@ def check_throughput_modes(lib, n_games, cfg_kwargs, max_plies, xp, leaves=4, ne
 
     multi = SelfPlay(n_games, cfg, lib=lib)
     multi.set_mode(0, leaves)
-    info_multi = multi.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    info_multi = multi.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
     recs = multi.policy_records()
     hist = multi.env.history()
     for g in range(n_games):
@@ -447,7 +478,7 @@ def check_throughput_modes(lib, n_games, cfg_kwargs, max_plies, xp, leaves=4, ne
     # determinism of the multi-leaf mode
     again = SelfPlay(n_games, cfg, lib=lib)
     again.set_mode(0, leaves)
-    again.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    again.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
     assert again.env.history() == hist
     _records_equal(again, multi)
     again.close()
@@ -516,7 +547,7 @@ def check_tree_reuse(lib, n_games, cfg_kwargs, max_plies, xp, net_seed=0):
     ev = stub_eval if xp == "numpy" else host_evaluator(stub_eval)
     c = SelfPlay(n_games, cfg, lib=lib)
     c.set_mode(MODE_TREE_REUSE, 1)
-    c.run_evaluator(ev, max_plies=max_plies, xp=xp)
+    c.run_evaluator(ev, max_plies=max_plies, buffers=_buffers(xp))
     assert c.env.history() == a.env.history()
     _records_equal(a, c)
     assert c.counters()["sims"] == a.counters()["sims"]
@@ -525,7 +556,7 @@ def check_tree_reuse(lib, n_games, cfg_kwargs, max_plies, xp, net_seed=0):
     d = SelfPlay(n_games, cfg, lib=lib)                       # with the forced-ply shortcut and 3 leaves per round
     d.set_mode(MODE_TREE_REUSE | MODE_SKIP_FORCED, 3)
     batched, _ = fixed_network(net_seed)
-    d.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, xp=xp)
+    d.run_evaluator(batched if xp == "numpy" else host_evaluator(batched), max_plies=max_plies, buffers=_buffers(xp))
     invariants(d, max_plies)
     d.close()
     sims_reuse = a.counters()["sims"]

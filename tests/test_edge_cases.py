@@ -58,6 +58,51 @@ def _capacity_suite(lib):
     assert len(ok.policy_records()[0]) == 2
 
 
+def _mode_suite(lib, xp):
+    """bk_selfplay_set_mode called repeatedly with a growing leaves_per_round, after tree reuse and after a packed
+    gather (round-1 advisor finding: the re-allocation freed buffers it did not own), and an evaluator whose policy
+    is <= 0 everywhere: reported as BK_ERR_STATE, nothing played or recorded (the reference would unwrap None)."""
+    from blokus_self_play import MODE_TREE_REUSE
+    cfg = Config(sims_per_move=24, sample_moves=4, c_base=19652, c_init=1.25, dirichlet_alpha=0.3, exploration_fraction=0.25, seed=3)
+    if xp == "torch":
+        import torch
+        mk = lambda pl: (pl[:, 4].reshape(-1, 400).clone(), torch.full((pl.shape[0], 4), 0.25, device=pl.device))
+        bad = lambda pl: (torch.zeros((pl.shape[0], 400), device=pl.device), torch.full((pl.shape[0], 4), 0.25, device=pl.device))
+    else:
+        mk = lambda pl: (pl[:, 4].reshape(-1, 400).copy(), np.full((pl.shape[0], 4), 0.25, dtype=np.float32))
+        bad = lambda pl: (np.zeros((pl.shape[0], 400), dtype=np.float32), np.full((pl.shape[0], 4), 0.25, dtype=np.float32))
+    sp = SelfPlay(5, cfg, lib=lib)
+    sp.set_mode(MODE_TREE_REUSE, 1)
+    sp.run_evaluator(mk, max_plies=2, buffers=parity._buffers(xp))
+    assert all(len(r) == 2 for r in sp.policy_records())          # packed gather allocates its buffers
+    sp.set_mode(MODE_TREE_REUSE, 2)                               # first d_pend allocation
+    sp.run_evaluator(mk, max_plies=2, buffers=parity._buffers(xp))
+    sp.set_mode(MODE_TREE_REUSE, 6)                               # grows d_pend; nothing else may be freed
+    sp.run_evaluator(mk, max_plies=2, buffers=parity._buffers(xp))
+    sp.set_mode(0, 3)                                             # smaller K: reuses the allocation
+    sp.run_evaluator(mk, max_plies=2, buffers=parity._buffers(xp))
+    recs = sp.policy_records()
+    assert all(len(r) == 8 and all(int(v.sum()) == 24 for _, v in r) for r in recs)
+    sp.close()
+    for leaves in (1, 4):
+        z = SelfPlay(3, cfg, lib=lib)
+        z.set_mode(0, leaves)
+        with pytest.raises(BkError) as e:
+            z.run_evaluator(bad, max_plies=1, buffers=parity._buffers(xp))
+        assert e.value.code == -5 and "no selectable child" in str(e.value)
+        assert [len(h) for h in z.env.history()] == [0, 0, 0]    # nothing was played from the failed search
+        z.close()
+
+
+def test_emu_set_mode_regrow_and_dead_policy(emu_lib):
+    _mode_suite(emu_lib, "numpy")
+
+
+@pytest.mark.gpu
+def test_gpu_set_mode_regrow_and_dead_policy(cuda_lib):
+    _mode_suite(cuda_lib, "torch")
+
+
 def test_emu_edge_cases(emu_lib, orc):
     _edge_suite(emu_lib, orc)
 

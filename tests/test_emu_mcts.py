@@ -31,7 +31,7 @@ def test_emu_external_stub_equals_fused_kernel(emu_lib, orc):
     a = SelfPlay(2, Config(**kw), first_game_id=1, lib=emu_lib)
     a.run_stub(4)
     b = SelfPlay(2, Config(**kw), first_game_id=1, lib=emu_lib)
-    b.run_evaluator(lambda pl: (pl[:, 4].reshape(-1, 400).copy(), np.full((pl.shape[0], 4), 0.25, dtype=np.float32)), 4, xp="numpy")
+    b.run_evaluator(lambda pl: (pl[:, 4].reshape(-1, 400).copy(), np.full((pl.shape[0], 4), 0.25, dtype=np.float32)), 4, buffers=parity.HostBuffers())
     assert a.env.history() == b.env.history()
     for ra, rb in zip(a.policy_records(), b.policy_records()):
         for (t1, v1), (t2, v2) in zip(ra, rb):
@@ -110,7 +110,7 @@ def test_emu_dense_rows_across_scan_chunks(emu_lib, orc):
             np.tile(np.array([0.4, 0.3, 0.2, 0.1], np.float32), (pl.shape[0], 1))
     a = SelfPlay(n, cfg, lib=emu_lib)
     a.set_mode(0, 2)
-    a.run_evaluator(ev, max_plies=1, xp="numpy")
+    a.run_evaluator(ev, max_plies=1, buffers=parity.HostBuffers())
     assert calls[0] == n and max(calls) <= 2 * n            # the root round is one row per game; later rounds are dense
     roots = a.last_root()
     for g in (1, 255, 256, 257, n - 1):

@@ -40,7 +40,7 @@ e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 evals = 0
 dense = a.leaves > 1
 for r in range(a.warmup + a.rounds):
-    rows = sp.leaf_rows() if dense else a.games       # multi-leaf mode: the evaluator batch is dense (no empty slots)
+    rows = sp.leaf_rows()                              # the evaluator batch is dense (no finished games, no empty slots)
     e0.record()
     policy, value = ev(planes[:rows])
     policy, value = policy.contiguous(), value.contiguous()
