@@ -97,6 +97,14 @@ _SIGNATURES = {
     "bk_env_playout_counters": (C.c_int, [_P, _P]),
     "bk_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "bk_conv3x3_bf16_in": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "bk_evaluator_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "bk_evaluator_destroy": (None, [_P]),
+    "bk_evaluator_max_rows": (C.c_int, [_P]),
+    "bk_evaluator_forward": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "bk_selfplay_run_network": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "bk_eval_pack_planes": (C.c_int, [_P, C.c_int, _P, _P]),
+    "bk_env_board_state_nhwc": (C.c_int, [_P, _P]),
+    "bk_eval_heads": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "bk_selfplay_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(BkConfig), C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "bk_selfplay_destroy": (None, [_P]),
     "bk_selfplay_reset": (C.c_int, [_P, C.c_uint32]),

@@ -37,9 +37,10 @@ def _head(width: int, tail=()) -> nn.Sequential:
 class ResNet(nn.Module):
     """ResNet(blocks, width): boards[B,5,20,20] -> (policy[B,400], value[B,4]); argument order of model/resnet.py:44."""
 
-    def __init__(self, blocks: int, width: int):
+    def __init__(self, blocks: int, width: int, custom_filters: bool = False):
         super().__init__()
         self.blocks, self.width = blocks, width
+        self.custom_filters = custom_filters      # accepted and unused, as in the reference (model/resnet.py:44-49; training.py:169)
         self.input = nn.Conv2d(5, width, 3, padding=1)
         self.res_blocks = nn.ModuleList(ResidualBlock(width, width) for _ in range(blocks))
         self.policy_head = _head(width)

@@ -180,6 +180,15 @@ class SelfPlay:
             plies += 1
         return {"plies": plies, "rounds": rounds}
 
+    def run_network(self, evaluator, max_plies: int = -1) -> dict:
+        """training_game() for every client with a native network evaluator (tc_resnet.TensorCoreLeafEvaluator, a
+        `bk_evaluator`): the whole round — planes, network, expand + backup — stays inside the library
+        (bk_selfplay_run_network); the host reads 8 bytes per round."""
+        evaluator.reserve(self.n * self.leaves_per_round)
+        rounds, evals = C.c_int64(0), C.c_int64(0)
+        self.lib.check(self.lib.bk_selfplay_run_network(self._h, evaluator.handle, int(max_plies), C.byref(rounds), C.byref(evals)))
+        return {"rounds": rounds.value, "evals": evals.value, "ms": self.last_kernel_ms()}
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0)
         self.lib.check(self.lib.bk_selfplay_last_kernel_ms(self._h, C.byref(ms)))

@@ -1,13 +1,19 @@
-"""Hand-written tensor-core leaf evaluator: the ResNet trunk's 3x3 convolutions run on
-`bk_conv3x3_bf16` (tcgen05 / TMEM / TMA, csrc/bk_conv.cu); the 5-channel input convolution and the two tiny heads
-stay in PyTorch.  BatchNorm (eval mode) is folded into the convolution weights and bias:
+"""Hand-written tensor-core leaf evaluator: the reference's `ResNet(blocks, 256)`
+(model/resnet.py:44-94, eval mode) as ONE native object of the C ABI (`bk_evaluator_*`, csrc/bk_eval.cu): input
+packing, the 2*blocks+1 tcgen05 convolutions and the fused heads all run on this library's kernels — PyTorch is only
+used here, once, to read the model's parameters and fold the BatchNorms:
+
     y = gamma * (conv(x) + b - mean) / sqrt(var + eps) + beta  =  conv_{w * s}(x) + ((b - mean) * s + beta),  s = gamma / sqrt(var + eps)
-Activations stay in the kernel's zero-padded NHWC bf16 layout [batch*441][256] for the whole trunk."""
+
+`TensorCoreLeafEvaluator` is callable like `resnet.LeafEvaluator` (planes -> policy, value on CUDA tensors) so it plugs
+into `SelfPlay.run_evaluator`; `SelfPlay.run_network(evaluator)` runs whole games with no Python in the round at all.
+The stand-alone operators (`conv3x3`, padded-layout helpers) remain for tests and probes."""
 from __future__ import annotations
 
 import ctypes as C
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -48,70 +54,92 @@ def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias: torch.Tensor, residual: Opt
     return y
 
 
-def conv3x3_in(x: torch.Tensor, w9: torch.Tensor, bias: torch.Tensor, relu: bool, batch: int, out: torch.Tensor, lib=None):
-    """Narrow-input form (in_channels = x.shape[1] in {64,128,192,256}), no residual."""
-    lib = lib or _lib.default_lib()
-    stream = torch.cuda.current_stream(x.device).cuda_stream
-    lib.check(lib.bk_conv3x3_bf16_in(C.c_void_p(x.data_ptr()), C.c_void_p(w9.data_ptr()), C.c_void_p(bias.data_ptr()),
-                                     C.c_void_p(out.data_ptr()), batch, x.shape[1], 1 if relu else 0, C.c_void_p(stream)))
-    return out
+def _bf16_host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to(torch.bfloat16).contiguous().view(torch.int16).cpu().numpy()
 
 
-def _bn_scalar(bn: torch.nn.BatchNorm2d):
+def _f32_host(t: torch.Tensor) -> np.ndarray:
+    return np.ascontiguousarray(t.detach().float().cpu().numpy())
+
+
+def _head_affine(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d):
     s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-    return s, bn.bias - bn.running_mean * s
+    return s, conv.bias * s + bn.bias - bn.running_mean * s
 
 
 class TensorCoreLeafEvaluator:
-    """Callable evaluator for SelfPlay.run_evaluator; same contract as resnet.LeafEvaluator (eval mode).
+    """The network on the device as a `bk_evaluator`; callable on CUDA planes [R,5,20,20] -> (policy [R,400], value [R,4]).
+    max_rows = the largest batch it will be asked to evaluate (activation buffers are sized for it; it grows on demand
+    when called with a larger batch)."""
 
-    Every 3x3 convolution — the 5->256 input layer (planes zero-extended to 64 channels) and the 2*blocks
-    trunk layers — runs on the hand-written tcgen05 kernel, activations never leave the padded NHWC bf16
-    layout; the two 1x1 head convolutions are one [B*441, 256] x [256, 2] product on that layout, and the
-    remaining head arithmetic (scalar BN, ReLU, masked softmax, Linear(400, 4), tanh, softmax) is on B x 400."""
-
-    def __init__(self, model: ResNet, lib=None):
+    def __init__(self, model: ResNet, lib=None, max_rows: int = 1024, device: Optional[int] = None):
         if model.width != 256:
             raise ValueError("the tcgen05 trunk kernel is built for width 256 (BASELINE.json config 4)")
-        self.model = model.eval()
         self.lib = lib or _lib.default_lib()
+        self.model = model.eval()
+        p = next(model.parameters())
+        self.device = int(device if device is not None else (p.device.index or 0) if p.is_cuda else 0)
         with torch.no_grad():
-            self.blocks = [(fold_conv_bn(b.conv1, b.bn1), fold_conv_bn(b.conv2, b.bn2)) for b in model.res_blocks]
-            w_in = torch.zeros((256, 64, 3, 3), dtype=model.input.weight.dtype, device=model.input.weight.device)
+            w_in = torch.zeros((256, 64, 3, 3), dtype=torch.float32, device=p.device)
             w_in[:, :5] = model.input.weight
-            self.w_in = w_in.permute(2, 3, 0, 1).reshape(9, 256, 64).to(torch.bfloat16).contiguous()
-            self.b_in = model.input.bias.float().contiguous()
-            pc, pbn = model.policy_head[0], model.policy_head[1]
-            vc, vbn = model.value_head[0], model.value_head[1]
-            self.w_heads = torch.cat([pc.weight.reshape(1, 256), vc.weight.reshape(1, 256)], 0).t().to(torch.bfloat16).contiguous()
-            ps, pb = _bn_scalar(pbn)
-            vs, vb = _bn_scalar(vbn)
-            self.head_scale = torch.cat([ps, vs]).float()
-            self.head_shift = torch.cat([pc.bias * ps + pb, vc.bias * vs + vb]).float()
-            self.lin = model.value_head[4]
-        self._bufs = {}
+            folded = [fold_conv_bn(c, b) for blk in model.res_blocks for c, b in ((blk.conv1, blk.bn1), (blk.conv2, blk.bn2))]
+            ps, pb = _head_affine(model.policy_head[0], model.policy_head[1])
+            vs, vb = _head_affine(model.value_head[0], model.value_head[1])
+            lin = model.value_head[4]
+            self._params = dict(
+                w_in=_bf16_host(w_in.permute(2, 3, 0, 1).reshape(9, 256, 64)), b_in=_f32_host(model.input.bias),
+                w_blk=np.stack([_bf16_host(w) for w, _ in folded]) if folded else np.zeros(1, dtype=np.int16),
+                b_blk=np.stack([_f32_host(b) for _, b in folded]) if folded else np.zeros(1, dtype=np.float32),
+                head_w=_f32_host(torch.cat([model.policy_head[0].weight.reshape(1, 256), model.value_head[0].weight.reshape(1, 256)])),
+                head_affine=_f32_host(torch.cat([ps, pb, vs, vb])), lin_w=_f32_host(lin.weight), lin_b=_f32_host(lin.bias))
+        self.blocks = len(model.res_blocks)
+        self._h = None
+        self._create(max_rows)
 
-    @torch.no_grad()
+    def _create(self, max_rows: int) -> None:
+        self.close()
+        q = self._params
+        h = C.c_void_p()
+        ptr = lambda a: C.c_void_p(a.ctypes.data)
+        self.lib.check(self.lib.bk_evaluator_create(self.device, self.blocks, int(max_rows), ptr(q["w_in"]), ptr(q["b_in"]),
+                                                    ptr(q["w_blk"]), ptr(q["b_blk"]), ptr(q["head_w"]), ptr(q["head_affine"]),
+                                                    ptr(q["lin_w"]), ptr(q["lin_b"]), C.byref(h)))
+        self._h = h
+        self.max_rows = int(max_rows)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self.lib.bk_evaluator_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def reserve(self, rows: int) -> None:
+        if rows > self.max_rows:
+            self._create(rows)
+
+    def forward(self, planes: torch.Tensor, debug: bool = False):
+        """`model(boards)`; with debug=True also the pre-softmax head outputs (policy_head(x) [R,400], value_head(x) [R,4])."""
+        rows = int(planes.shape[0])
+        self.reserve(rows)
+        planes = planes.to(dtype=torch.float32).contiguous()
+        policy = torch.empty((rows, 400), dtype=torch.float32, device=planes.device)
+        value = torch.empty((rows, 4), dtype=torch.float32, device=planes.device)
+        logits = torch.empty((rows, 400), dtype=torch.float32, device=planes.device) if debug else None
+        vtanh = torch.empty((rows, 4), dtype=torch.float32, device=planes.device) if debug else None
+        stream = torch.cuda.current_stream(planes.device).cuda_stream
+        opt = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self.lib.check(self.lib.bk_evaluator_forward(self._h, C.c_void_p(planes.data_ptr()), rows, opt(policy), opt(value),
+                                                     opt(logits), opt(vtanh), C.c_void_p(stream)))
+        return (policy, value, logits, vtanh) if debug else (policy, value)
+
     def __call__(self, planes: torch.Tensor):
-        batch = planes.shape[0]
-        key = planes.device
-        if key not in self._bufs or self._bufs[key][2] < batch:      # grow-only buffers: batch sizes vary round to round
-            rows = batch * PAD * PAD
-            self._bufs[key] = ([torch.zeros((rows, 256), dtype=torch.bfloat16, device=planes.device) for _ in range(3)],
-                               torch.zeros((rows, 64), dtype=torch.bfloat16, device=planes.device), batch)
-        (a, t, b), x64, _cap = self._bufs[key]
-        rows = batch * PAD * PAD
-        a, t, b, x64 = a[:rows], t[:rows], b[:rows], x64[:rows]
-        x64.view(batch, PAD, PAD, 64)[:, :20, :20, :5] = planes.permute(0, 2, 3, 1).to(torch.bfloat16)
-        conv3x3_in(x64, self.w_in, self.b_in, False, batch, out=a, lib=self.lib)      # model.input (no BN / ReLU, resnet.py:79)
-        for (w1, b1), (w2, b2) in self.blocks:
-            conv3x3(a, w1, b1, None, True, batch, out=t, lib=self.lib)                 # relu(bn1(conv1(x)))
-            conv3x3(t, w2, b2, a, True, batch, out=b, lib=self.lib)                    # relu(bn2(conv2(.)) + x)
-            a, b = b, a
-        heads = (a @ self.w_heads).float().view(batch, PAD, PAD, 2)[:, :20, :20, :]     # both 1x1 head convolutions
-        heads = torch.relu(heads * self.head_scale + self.head_shift).reshape(batch, 400, 2)
-        legal = planes[:, 4].reshape(batch, -1)
-        logits = heads[:, :, 0]
-        policy = torch.softmax(logits * legal + (1 - legal) * -1e9, dim=1) * legal
-        value = torch.softmax(torch.tanh(self.lin(heads[:, :, 1])), dim=1)
-        return policy, value
+        return self.forward(planes)

@@ -47,3 +47,29 @@ struct bk_env {
 
 // implemented in bk_env.cu, used by bk_mcts.cu
 int bk_env_alloc(int n_games, int device, cudaStream_t stream, bk_env** out);
+
+// implemented in bk_conv.cu, used by bk_eval.cu: one 3x3 convolution on the padded NHWC bf16 layout
+int bk_conv_launch(const void* dev_x, const void* dev_w, const float* dev_bias, const void* dev_residual, void* dev_y,
+                   int batch, int in_channels, int relu, void* cuda_stream);
+
+// The policy/value network of model/resnet.py:44-94 (eval mode, BatchNorm folded) resident on one device:
+// weights, the three ping-pong activation matrices and the first layer's input, all in the convolution
+// kernel's padded NHWC bf16 layout.  Defined here because bk_mcts.cu drives it inside the self-play loop.
+struct bk_evaluator {
+    int device = 0;
+    int blocks = 0;
+    int cap_rows = 0;                 // positions per forward pass the buffers hold
+    uint16_t* d_w_in = nullptr;       // bf16 [9][256][64]
+    float* d_b_in = nullptr;          // [256]
+    uint16_t* d_w_blk = nullptr;      // bf16 [2*blocks][9][256][256]
+    float* d_b_blk = nullptr;         // [2*blocks][256]
+    float* d_head = nullptr;          // head_w [2][256], head_affine [4], lin_w [4][400], lin_b [4]
+    uint16_t* d_act[3] = {nullptr, nullptr, nullptr};   // bf16 [cap_rows*441][256]
+    uint16_t* d_x64 = nullptr;        // bf16 [cap_rows*441][64]
+    float* d_policy = nullptr;        // [cap_rows][400]   (outputs of the fused self-play loop)
+    float* d_value = nullptr;         // [cap_rows][4]
+};
+
+// implemented in bk_eval.cu: the network on the positions already written to ev->d_x64 (rows of them)
+int bk_evaluator_forward_x64(bk_evaluator* ev, int rows, float* dev_policy, float* dev_value, float* dev_logits,
+                             float* dev_vtanh, cudaStream_t stream);

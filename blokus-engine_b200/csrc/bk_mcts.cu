@@ -9,6 +9,7 @@
 
 #include "bk_host.h"
 #include "bk_mcts_kernels.cuh"
+#include "bk_eval_kernels.cuh"
 
 struct bk_selfplay {
     int n = 0;
@@ -36,6 +37,7 @@ struct bk_selfplay {
     float* d_prior = nullptr;
     unsigned long long* d_counters = nullptr;  // [8], cumulative
     uint8_t* d_stage = nullptr;       // [n][400 * 16] gather staging for last_root
+    int32_t* d_round = nullptr;       // [4] per-round scalars of the fused network loop
     int64_t* d_ply_off = nullptr;     // [n + 1] prefix of plies per game (training tensors)
     int64_t* d_pack_off = nullptr;    // [2][n + 1] prefixes of plies / policy entries per game (packed results)
     int64_t* d_pack_ptr = nullptr;    // [pack_plies + 1]
@@ -101,10 +103,11 @@ __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl
 // The evaluator batch is DENSE in every mode — game g's outstanding positions (one in the exact mode, up to
 // leaves_per_round in the multi-leaf mode) occupy rows slot_base[g] .. slot_base[g + 1) in (game, slot) order,
 // slot_base[n] = rows to evaluate — so the evaluator never works on finished games or empty slots.  One CTA, chunked scan.
-__global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n, int vl) {
+__global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n, int vl, int32_t* __restrict__ round_out) {
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0u;
+    __shared__ uint32_t waiting;                     // games that need the next expand_backup call (incl. kept trees resuming)
+    if (threadIdx.x == 0) { carry = 0u; waiting = 0u; }
     __syncthreads();
     for (int c0 = 0; c0 < n; c0 += 256) {
         const int g = c0 + int(threadIdx.x);
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n, int vl)
         if (g < n) {
             const uint32_t k = pl.hdr[g].pend_kind;
             cnt = k == BK_PEND_ROOT ? 1u : (k == BK_PEND_LEAF ? (vl ? pl.hdr[g].pend_count : 1u) : 0u);
+            if (k == BK_PEND_ROOT || k == BK_PEND_LEAF || k == BK_PEND_RESUME) atomicAdd(&waiting, 1u);
         }
         uint32_t incl = cnt;
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -126,7 +130,31 @@ __global__ void __launch_bounds__(256) k_sp_slot_scan(BkPools pl, int n, int vl)
         if (threadIdx.x == 255) carry = before + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) pl.slot_base[n] = carry;
+    if (threadIdx.x == 0) {
+        pl.slot_base[n] = carry;
+        if (round_out) { round_out[0] = int32_t(carry); round_out[1] = int32_t(waiting); }   // rows to evaluate, games waiting
+    }
+}
+
+// the pending positions' planes written straight into the evaluator's first-layer input (padded NHWC bf16), dense rows
+__global__ void __launch_bounds__(256) k_sp_planes_nhwc(BkSearchCfg cfg, BkPools pl, int n, int vl, uint16_t* __restrict__ x64) {
+    const int K = int(cfg.leaves_per_round);
+    const int g = blockIdx.x / K, j = blockIdx.x % K;
+    if (g >= n) return;
+    const BkSearchHdr* h = &pl.hdr[g];
+    bool pend = h->pend_kind == BK_PEND_ROOT || h->pend_kind == BK_PEND_LEAF;
+    uint32_t slot = h->n_nodes;
+    if (vl) {
+        if (h->pend_kind == BK_PEND_ROOT) { pend = j == 0; slot = 0u; }
+        else if (h->pend_kind == BK_PEND_LEAF) {
+            pend = uint32_t(j) < h->pend_count;
+            if (pend) slot = pl.pend[size_t(g) * cfg.leaves_per_round + j].slot;
+        }
+    }
+    if (!pend) return;
+    const size_t row = size_t(pl.slot_base[g]) + size_t(j);
+    kb_planes_nhwc(&bk_tree_of(pl, cfg, g).nodes[slot], reinterpret_cast<uint4*>(x64 + row * BK_PAD_IMAGE * BK_EVAL_IN_CH), threadIdx.x,
+                   blockDim.x);
 }
 
 // planes of every game's pending position, float32 [n][5][20][20]; counts pending games
@@ -345,6 +373,7 @@ static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_
     BK_CUDA(cudaMalloc(&sp->d_pol_visits, sizeof(uint32_t) * size_t(d.policy_cap) * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 8));
     BK_CUDA(cudaMalloc(&sp->d_stage, size_t(n_games) * 400 * 16));
+    BK_CUDA(cudaMalloc(&sp->d_round, sizeof(int32_t) * 4));
     BK_CUDA(cudaMalloc(&sp->d_slot_base, sizeof(uint32_t) * (size_t(n_games) + 1)));
     BK_CUDA(cudaMemsetAsync(sp->d_slot_base, 0, sizeof(uint32_t) * (size_t(n_games) + 1), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games), sp->env->stream));
@@ -383,6 +412,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaFree(sp->d_scratch); cudaFree(sp->d_hdr); cudaFree(sp->d_pol_off); cudaFree(sp->d_pol_tile);
     cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
     cudaFree(sp->d_stage);
+    cudaFree(sp->d_round);
     cudaFree(sp->d_ply_off);
     cudaFree(sp->d_pend);
     cudaFree(sp->d_remap);
@@ -494,7 +524,7 @@ int bk_selfplay_leaf_planes(bk_selfplay* sp, float* dev_planes, int32_t* pending
     cudaStream_t st = sp->env->stream;
     int32_t* d_cnt = sp->env->d_i32 + 2;
     BK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t), st));
-    BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n, sp->use_vl ? 1 : 0);
+    BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n, sp->use_vl ? 1 : 0, static_cast<int32_t*>(nullptr));
     BK_LAUNCH(k_sp_planes, sp->n * int(sp->dcfg.leaves_per_round), 256, st, sp->dcfg, pools_of(sp), sp->n,
               sp->use_vl ? 1 : 0, dev_planes, d_cnt);
     BK_CUDA(cudaGetLastError());
@@ -548,6 +578,63 @@ int bk_selfplay_end_ply(bk_selfplay* sp) {
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     return sp_check_errors(sp);
+}
+
+int bk_selfplay_run_network(bk_selfplay* sp, bk_evaluator* ev, int max_plies, int64_t* rounds_out, int64_t* evals_out) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    if (!ev) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_run_network: null evaluator");
+    if (ev->device != sp->device) return bk_fail(BK_ERR_INVALID_ARG, "bk_selfplay_run_network: evaluator lives on another device");
+    if (int64_t(ev->cap_rows) < int64_t(sp->n) * int64_t(sp->dcfg.leaves_per_round))
+        return bk_fail(BK_ERR_CAPACITY, "bk_selfplay_run_network: evaluator max_rows < n_games * leaves_per_round");
+    cudaStream_t st = sp->env->stream;
+    int32_t* d_round = sp->d_round;                  // {rows, games waiting}, written by the slot scan
+    const int vl = sp->use_vl ? 1 : 0;
+    const int slots = sp->n * int(sp->dcfg.leaves_per_round);
+    int64_t rounds = 0, evals = 0;
+    // enqueue: dense row assignment + the waiting positions' planes into the network's input; then one 8-byte read
+    auto collect = [&](int32_t (&h)[2]) -> int {
+        BK_LAUNCH(k_sp_slot_scan, 1, 256, st, pools_of(sp), sp->n, vl, d_round);
+        BK_LAUNCH(k_sp_planes_nhwc, slots, 256, st, sp->dcfg, pools_of(sp), sp->n, vl, ev->d_x64);
+        BK_CUDA(cudaGetLastError());
+        BK_CUDA(cudaMemcpyAsync(h, d_round, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BK_CUDA(cudaStreamSynchronize(st));
+        return BK_OK;
+    };
+    BK_CUDA(cudaEventRecord(sp->ev0, st));
+    for (int ply = 0; max_plies < 0 || ply < max_plies; ++ply) {
+        int32_t live = 0;
+        rc = bk_selfplay_live_games(sp, &live);
+        if (rc) return rc;
+        if (!live) break;
+        rc = bk_selfplay_begin_ply(sp);
+        if (rc) return rc;
+        int32_t h[2] = {0, 0};
+        rc = collect(h);
+        if (rc) return rc;
+        while (h[1] > 0) {
+            if (h[0] > 0) {
+                rc = bk_evaluator_forward_x64(ev, h[0], ev->d_policy, ev->d_value, nullptr, nullptr, st);
+                if (rc) return rc;
+                evals += h[0];
+            }
+            if (sp->use_vl)
+                BK_LAUNCH(k_sp_step_vl, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, ev->d_policy, ev->d_value, sp->d_counters);
+            else
+                BK_LAUNCH(k_sp_step, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->n, ev->d_policy, ev->d_value, sp->d_counters);
+            ++rounds;
+            rc = collect(h);
+            if (rc) return rc;
+        }
+        rc = bk_selfplay_end_ply(sp);
+        if (rc) return rc;
+    }
+    BK_CUDA(cudaEventRecord(sp->ev1, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(cudaEventElapsedTime(&sp->last_ms, sp->ev0, sp->ev1));
+    if (rounds_out) *rounds_out = rounds;
+    if (evals_out) *evals_out = evals;
+    return BK_OK;
 }
 
 int bk_selfplay_set_stream(bk_selfplay* sp, void* cuda_stream) {

@@ -301,6 +301,49 @@ int bk_conv3x3_bf16(const void* dev_x, const void* dev_w, const float* dev_bias,
 int bk_conv3x3_bf16_in(const void* dev_x, const void* dev_w, const float* dev_bias, void* dev_y, int batch,
                        int in_channels, int relu, void* cuda_stream);
 
+/* ---- leaf evaluator as one native object (BASELINE.json config 4) ------------------------ */
+/* The reference's policy/value network, `ResNet(blocks, 256)` of model/resnet.py:44-94, in eval mode, entirely on this
+ * library's kernels: input packing -> 2*blocks+1 tcgen05 convolutions -> one fused head kernel (both 1x1 head
+ * convolutions + BatchNorm + ReLU, the policy's masked softmax x mask, the value's Linear(400,4) + tanh + softmax).
+ * It replaces what the reference's inference server computes per batch (model/training.py:43-67).
+ * Parameters are HOST pointers (copied once), BatchNorm folded by the caller (scale s = gamma / sqrt(var + eps)):
+ *   w_in      bf16 [9][256][64]   model.input.weight, tap = ky*3 + kx, the 5 input planes zero-extended to 64
+ *   b_in      f32  [256]          model.input.bias                (no BN / ReLU after it, resnet.py:79)
+ *   w_blocks  bf16 [2*blocks][9][256][256]   conv1, conv2 of each block times their BN scale
+ *   b_blocks  f32  [2*blocks][256]           (conv bias - running_mean) * s + beta
+ *   head_w    f32  [2][256]       policy_head[0].weight, value_head[0].weight (1x1 convolutions)
+ *   head_affine f32 [4]           policy {s, conv_bias*s + beta - mean*s}, value {same}: head = relu(dot * a0 + a1)
+ *   lin_w     f32  [4][400], lin_b f32 [4]   value_head[4] (Linear)
+ * max_rows = positions per forward pass the activation buffers hold (3 x max_rows x 441 x 512 B). */
+typedef struct bk_evaluator bk_evaluator;
+int bk_evaluator_create(int device, int blocks, int max_rows, const void* w_in, const float* b_in, const void* w_blocks,
+                        const float* b_blocks, const float* head_w, const float* head_affine, const float* lin_w,
+                        const float* lin_b, bk_evaluator** out);
+void bk_evaluator_destroy(bk_evaluator* ev);
+int bk_evaluator_max_rows(const bk_evaluator* ev);
+/* `model(boards)` (resnet.py:69-94): dev_planes f32 [rows][5][20][20] -> dev_policy f32 [rows][400] (mover frame, zero
+ * on illegal tiles), dev_value f32 [rows][4] (relative seats).  dev_logits [rows][400] / dev_vtanh [rows][4] (may be
+ * NULL) receive the pre-softmax head outputs (policy_head(x), value_head(x)) for parity checks.  All DEVICE memory;
+ * enqueued on cuda_stream, no synchronisation. */
+int bk_evaluator_forward(bk_evaluator* ev, const float* dev_planes, int rows, float* dev_policy, float* dev_value,
+                         float* dev_logits, float* dev_vtanh, void* cuda_stream);
+/* training_game() (simulation.rs:267-296) for every client with this network as the evaluator, up to max_plies plies
+ * (< 0: to the end).  The whole round stays on the device: the pending positions' planes are written straight into
+ * the first convolution's input (no float planes), the network runs, expand + backup consume its outputs; per round
+ * the host reads back 8 bytes (rows to evaluate, games waiting).  Honours bk_selfplay_set_mode (dense rows, multi-leaf
+ * rounds, forced-ply shortcut, tree reuse).  rounds_out / evals_out (may be NULL): evaluator rounds, positions evaluated. */
+int bk_selfplay_run_network(bk_selfplay* sp, bk_evaluator* ev, int max_plies, int64_t* rounds_out, int64_t* evals_out);
+/* The evaluator's two non-convolution stages as stand-alone operators on DEVICE memory (building blocks, like
+ * bk_conv3x3_bf16): float planes [rows][5][20][20] -> the first convolution's input x64 bf16 [rows*441][64] (which the
+ * caller zero-initialised once: only channels 0..7 of the 400 real cells are written), and the fused heads on the
+ * trunk's output act bf16 [rows*441][256]; dev_head_params f32 [2120] = head_w[512], head_affine[4], lin_w[1600], lin_b[4]. */
+int bk_eval_pack_planes(const float* dev_planes, int rows, void* dev_x64, void* cuda_stream);
+/* Game::get_board_state (game.rs:283-311) of every game of the batch written directly in that input layout
+ * (dev_x64 bf16 [n_games*441][64], zero-initialised by the caller); synchronises the batch's stream. */
+int bk_env_board_state_nhwc(bk_env* env, void* dev_x64);
+int bk_eval_heads(const void* dev_act, const void* dev_x64, const float* dev_head_params, int rows, float* dev_policy,
+                  float* dev_value, float* dev_logits, float* dev_vtanh, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,13 +77,12 @@ def test_gpu_selfplay_with_resnet_config4_shape(cuda_lib, orc):
 
 
 @pytest.mark.gpu
-def test_tensor_core_trunk_matches_torch_model(cuda_lib):
-    """the hand-written tcgen05 trunk against the same ResNet(width 256) evaluated by PyTorch in
-    fp32.  bf16 operands / bf16 activations between layers: tolerance 3e-2 absolute on the softmax outputs (the same
-    bound as the cuDNN bf16 path above), and each convolution alone within bf16 rounding of an fp32 reference."""
+def test_tensor_core_convolution_matches_fp32(cuda_lib):
+    """one tcgen05 convolution (fused bias + residual + ReLU) within bf16 rounding of an fp32
+    reference on bf16-rounded operands, over the CTA-pair kernel's corner-case batch sizes.  The whole network is
+    checked against the reference's model in test_tensor_core_resnet20x256_against_reference_model."""
     import torch.nn.functional as F
-    from blokus_self_play.resnet import ResNet, LeafEvaluator
-    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator, to_padded_nhwc, from_padded_nhwc, conv3x3, fold_conv_bn
+    from blokus_self_play.tc_resnet import to_padded_nhwc, from_padded_nhwc, conv3x3
     torch.manual_seed(3)
     dev = torch.device("cuda", 0)
     # one convolution, fused residual + ReLU, odd batch (tail tile) — fp32 reference on bf16-rounded operands
@@ -101,18 +100,129 @@ def test_tensor_core_trunk_matches_torch_model(cuda_lib):
         assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item()), B
         pad = y.reshape(B, 21, 21, 256)
         assert pad[:, 20].abs().max().item() == 0 and pad[:, :, 20].abs().max().item() == 0
-    # whole evaluator
-    model = ResNet(3, 256).to(dev).eval()
+
+
+GOLD20 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet_20x256.npz")
+
+
+def load_model20():
+    """ResNet(20,256) with the deterministic parameters of tests/resnet_params.py + the stored head calibration:
+    bit-identical to the model tests/golden/make_resnet20_golden.py evaluated with the reference's model/resnet.py."""
+    from blokus_self_play.resnet import ResNet
+    from resnet_params import make_state_dict, unpack_planes
+    z = np.load(GOLD20)
+    model = ResNet(20, 256)
+    sd = make_state_dict(model.state_dict(), int(z["seed"]))
+    for k in z.files:
+        if k.startswith("override/"):
+            sd[k[len("override/"):]] = torch.from_numpy(z[k]).float()
+    model.load_state_dict(sd, strict=True)
+    return model.eval(), z, unpack_planes(z["planes_bits"], int(z["n"]))
+
+
+def _report(name, data):
+    """Measured numbers of the parity tests, kept next to the other GPU evidence when run under gpurun."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, name), "w") as f:
+            json.dump(data, f, indent=1)
+
+
+def test_resnet20_parameters_are_reproducible():
+    """The regenerated parameters are the ones the golden script used: this repo's model, in fp32 on the CPU, reproduces
+    the reference model's stored outputs for the first positions (the GPU box repeats this for all 256)."""
+    model, z, planes = load_model20()
+    assert planes.shape == (256, 5, 20, 20) and set(np.unique(planes)) <= {0.0, 1.0}
+    assert sum(p.numel() for p in model.parameters()) == 23637578          # SURVEY: 23.64 M parameters
     with torch.no_grad():
-        for m in model.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.6, 1.4); m.weight.uniform_(0.6, 1.4); m.bias.normal_(0, 0.1)
-    z = np.load(GOLD)
-    planes = torch.from_numpy(z["planes"]).to(dev)
-    p_ref, v_ref = LeafEvaluator(model)(planes)
-    p_tc, v_tc = TensorCoreLeafEvaluator(model, lib=cuda_lib)(planes)
-    assert (p_tc - p_ref).abs().max().item() <= 3e-2 and (v_tc - v_ref).abs().max().item() <= 3e-2
-    assert torch.all(p_tc[planes[:, 4].reshape(len(planes), -1) == 0] == 0)
+        policy, value = model(torch.from_numpy(planes[:3]))
+    assert np.allclose(policy.numpy(), z["policy"][:3], atol=1e-6) and np.allclose(value.numpy(), z["value"][:3], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_tensor_core_resnet20x256_against_reference_model(cuda_lib):
+    """Row f2 at BASELINE.json config 4's real size.  Golden = the REFERENCE's model/resnet.py, ResNet(20,256), fp32 on
+    the CPU, 256 game positions.  (a) this repo's PyTorch model in fp32 on the GPU reproduces it to 1e-3 (cuDNN fp32,
+    TF32 off); (b) the hand-written tcgen05 evaluator (bf16 operands and activations, f32 accumulation) against it:
+    pre-softmax policy logits and value-head outputs, KL(policy_fp32 || policy_tc), top-1 agreement, |value| error.
+    bf16 is narrower than the reference's fp32 (sanctioned by SURVEY §7.5/§8d); this test QUANTIFIES the divergence
+    over all 41 layers instead of bounding softmax outputs absolutely."""
+    from blokus_self_play.resnet import LeafEvaluator
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    model, z, planes = load_model20()
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(planes).to(dev)
+    mask = planes[:, 4].reshape(len(planes), 400) > 0
+    model = model.to(dev)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            p32, v32 = LeafEvaluator(model)(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref_p, ref_v, ref_l, ref_t = z["policy"], z["value"], z["logits"], z["vtanh"]
+    err32 = float(np.abs(p32.cpu().numpy() - ref_p).max())
+    assert err32 <= 1e-3 and float(np.abs(v32.cpu().numpy() - ref_v).max()) <= 1e-3, err32
+    ev = TensorCoreLeafEvaluator(model, lib=cuda_lib, max_rows=256)
+    p, v, lg, vt = (t.cpu().numpy() for t in ev.forward(x, debug=True))
+    assert np.all(p[~mask] == 0) and np.allclose(p.sum(axis=1), 1.0, atol=1e-4) and np.allclose(v.sum(axis=1), 1.0, atol=1e-5)
+    scale = float(np.abs(ref_l[mask]).max())
+    logit_err = np.abs(lg - ref_l)[mask]
+    kl = np.array([float(np.sum(ref_p[i][mask[i]] * (np.log(ref_p[i][mask[i]] + 1e-30) - np.log(p[i][mask[i]] + 1e-30)))) for i in range(len(p))])
+    multi = mask.sum(axis=1) >= 2
+    top1 = float(np.mean(np.argmax(np.where(mask, lg, -1), axis=1)[multi] == np.argmax(np.where(mask, ref_l, -1), axis=1)[multi]))
+    srt = np.sort(np.where(mask, ref_l, -1e9), axis=1)
+    clear = multi & (srt[:, -1] - srt[:, -2] > 4 * float(logit_err.max()))          # positions whose fp32 winner is not a near-tie
+    top1_clear = float(np.mean(np.argmax(np.where(mask, lg, -1), axis=1)[clear] == np.argmax(np.where(mask, ref_l, -1), axis=1)[clear]))
+    res = {"positions": int(len(p)), "fp32_gpu_vs_reference_cpu_max_abs_policy": err32,
+           "logit_scale_max_abs": scale, "logit_max_abs_err": float(logit_err.max()), "logit_mean_abs_err": float(logit_err.mean()),
+           "logit_max_err_rel_to_scale": float(logit_err.max()) / scale,
+           "vtanh_max_abs_err": float(np.abs(vt - ref_t).max()), "value_max_abs_err": float(np.abs(v - ref_v).max()),
+           "policy_max_abs_err": float(np.abs(p - ref_p).max()), "kl_max": float(kl.max()), "kl_mean": float(kl.mean()),
+           "top1_agreement_positions_with_2plus_legal": top1, "positions_with_2plus_legal": int(multi.sum()),
+           "top1_agreement_clear_winner": top1_clear, "positions_clear_winner": int(clear.sum())}
+    _report("f2_parity_resnet20x256.json", res)
+    print(res)
+    assert res["logit_max_err_rel_to_scale"] <= 2e-2, res          # pre-softmax logits: max error relative to the logit range
+    assert res["kl_max"] <= 1e-2, res
+    assert res["value_max_abs_err"] <= 1e-2 and res["vtanh_max_abs_err"] <= 2e-2, res
+    assert top1_clear == 1.0 and top1 >= 0.97, res
+
+
+@pytest.mark.gpu
+def test_search_visit_distribution_fp32_vs_tensor_core(cuda_lib):
+    """What the bf16 evaluator does to the SEARCH: one config-3-shaped ply (800 sims, alpha 0.03, frac 0.25) of 32 games
+    on ResNet(20,256) with the fp32 PyTorch evaluator and with the tcgen05 evaluator (same seeds, same noise): L1
+    distance between the root visit distributions, and whether the most-visited child agrees."""
+    from blokus_self_play import SelfPlay, Config
+    from blokus_self_play.resnet import LeafEvaluator
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    model, _, _ = load_model20()
+    model = model.cuda()
+    cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03, exploration_fraction=0.25, seed=17)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        a = SelfPlay(32, cfg, lib=cuda_lib)
+        a.run_evaluator(LeafEvaluator(model), max_plies=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    b = SelfPlay(32, cfg, lib=cuda_lib)
+    info = b.run_network(TensorCoreLeafEvaluator(model, lib=cuda_lib, max_rows=32), max_plies=1)
+    assert info["rounds"] == 801
+    l1, same_best = [], []
+    for ra, rb in zip(a.policy_records(), b.policy_records()):
+        (ta, va), (tb, vb) = ra[0], rb[0]
+        assert np.array_equal(ta, tb) and int(va.sum()) == int(vb.sum()) == 800
+        l1.append(float(np.abs(va / 800.0 - vb / 800.0).sum()))
+        same_best.append(int(np.argmax(va) == np.argmax(vb)))
+    res = {"games": 32, "sims": 800, "l1_mean": float(np.mean(l1)), "l1_max": float(np.max(l1)), "same_most_visited": float(np.mean(same_best))}
+    _report("f2_search_l1_fp32_vs_tcgen05.json", res)
+    print(res)
+    assert res["l1_mean"] <= 0.25 and res["same_most_visited"] >= 0.75, res
+    a.close(); b.close()
 
 
 @pytest.mark.gpu

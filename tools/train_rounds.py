@@ -47,12 +47,17 @@ for rnd in range(a.rounds):
     model.eval()
     if a.width == 256:
         from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
-        ev = TensorCoreLeafEvaluator(model)                         # BatchNorm folded from the current weights
+        ev = TensorCoreLeafEvaluator(model, max_rows=a.games * a.leaves)   # BatchNorm folded from the current weights
     else:
         ev = LeafEvaluator(model)
     sp = SelfPlay(a.games, cfg, first_game_id=rnd * a.games)        # fresh global ids every round
     sp.set_mode(MODE_SKIP_FORCED if a.skip_forced else 0, a.leaves)
-    info = sp.run_evaluator(ev, max_plies=a.max_plies)
+    if a.width == 256:
+        info = sp.run_network(ev, max_plies=a.max_plies)            # the whole round inside the library
+        info["plies"] = max(len(h) for h in sp.env.history())
+        ev.close()
+    else:
+        info = sp.run_evaluator(ev, max_plies=a.max_plies)
     torch.cuda.synchronize()
     t1 = time.time()
     n_new = buffer.extend_from(sp)
