@@ -10,11 +10,21 @@ whatever advance_player / move generation it triggers.
   e2e       the same metric through the C-ABI with HOST buffers: H2D of the batch's game ids from pinned
             memory, the kernels, D2H of plies + scores + packed histories into pinned memory, every step
             (double-buffered over two handles: the copy-out of one batch overlaps the playout of the next)
-  roofline  dominant kernel k_playout against the measured HBM peak with SURVEY §8d's 708 B/move, plus the
-            integer-issue roofline that actually binds it (int_roofline)
+  roofline  dominant kernel k_playout against the roof that binds it: INT32 issue (bound "int32"), algorithmic
+            lane-ops = sum of 120*C_rem per move generation, peak = profiles/r02_int_peak.json (probed
+            on this pool with bk_probe_int_peak, clocks recorded) cross-checked live; `traffic` = measured DRAM
+            bytes per launch (ncu); hbm_note keeps the HBM view with that measured traffic
   cpu_baseline  the CPU oracle (C++ restatement of the reference algorithm) on the host cores, bounded sample
+  extra.env_sustained  the same step looped for >= 2 s with the clocks sampled inside the loop
+  extra.mcts           BASELINE's second metric (configs[2]: 1024 games, 800 sims/move, fixed priors): device-timed
+                       value, e2e (finished-game tuples read back to host memory inside the timed region, bytes
+                       declared) and a CPU sample on the SAME workload (complete games of the first ids)
+  extra.config5_shard  configs[4]'s per-GPU share, 8192 games to completion; at N > 1 rank 0 replays a slice of
+                       rank 1's ids and compares traces and payoffs
+  extra.leaf_eval      configs[3] building block: ResNet(20,256) on 1024 leaves per round, native evaluator
 
-`--impl reference` times that CPU restatement alone (the Rust reference cannot be built here: no rustc).
+`--impl reference` times the CPU restatement alone (the Rust reference cannot be built here: no rustc; probed at
+run time and recorded) for both metrics, so a ratio can be formed from two driver-run lines.
 """
 from __future__ import annotations
 
@@ -129,7 +139,12 @@ MCTS_CFG = dict(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, d
 
 def mcts_measure(local_rank: int, rank: int, plies: int):
     """Secondary metric (BASELINE.json configs[2]): 1024 games/GPU, 800 sims/move, fixed uniform priors,
-    Dirichlet alpha 0.03 / frac 0.25, the whole self-play loop on the device.  plies < 0: complete games."""
+    Dirichlet alpha 0.03 / frac 0.25, the whole self-play loop on the device.  plies < 0: complete games.
+    Two measurements of the same workload: device-timed (CUDA events round the one kernel) and end to end through
+    the C ABI — reset, the kernel, and the finished-game training tuples (packed policy records, packed histories,
+    plies, scores, payoffs) copied into HOST memory, all inside the host-timed region."""
+    import numpy as np
+    import torch
     from blokus_self_play import SelfPlay, Config
     sp = SelfPlay(MCTS_GAMES, Config(**MCTS_CFG), first_game_id=rank * MCTS_GAMES, device=local_rank)
     sp.run_stub(2)                      # warm-up (2 plies), then start over
@@ -141,25 +156,68 @@ def mcts_measure(local_rank: int, rank: int, plies: int):
     out["kernel_ms"] = ms
     out["plies"] = int(sum(len(h) for h in sp.env.history()))
     out["finished_games"] = int(sp.env.is_terminal().sum())
+    # end to end: the call a user of the drop-in makes (play_training_games without the per-ply Python tuples)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sp.reset()
+    sp.run_stub(plies)
+    ply_off, ply_ptr, tiles, visits = sp.policy_records_packed()
+    plies_h, scores_h, hist_h = sp.env.fetch()
+    pay = sp.env.payoff()
+    out["e2e_s"] = time.perf_counter() - t0
+    out["e2e_sims"] = sp.counters()["sims"] - c1["sims"]
+    out["e2e_d2h_bytes"] = int(ply_off.nbytes + ply_ptr.nbytes + tiles.nbytes + visits.nbytes + plies_h.nbytes + scores_h.nbytes
+                               + hist_h.nbytes + pay.nbytes)
+    out["e2e_h2d_bytes"] = 48           # the search configuration + first game id (bk_config)
+    out["e2e_policy_entries"] = int(len(tiles))
     sp.close()
     return out
 
 
-def mcts_large_batch_measure(local_rank: int, rank: int, games: int = 8192, plies: int = 8):
-    """BASELINE.json configs[4]'s per-GPU shape (8192 games, 800 sims/move, stub evaluator): the throughput regime of the
-    same kernel (20 resident games per SM) on a prefix of the games.  Never fails the bench: returns None on any error."""
+def config5_shard_measure(local_rank: int, rank: int, world: int, dist, games: int = 8192, check: int = 32):
+    """BASELINE.json configs[4]'s per-GPU share: `games` complete self-play games (800 sims/move, stub evaluator) in one
+    launch.  At N > 1 rank 0 then replays the first `check` ids of RANK 1's range as a separate small batch and compares
+    action traces and payoffs with what rank 1 produced inside its shard (results depend on the global id only)."""
+    import numpy as np
+    import torch
+    from blokus_self_play import SelfPlay, Config
     try:
-        from blokus_self_play import SelfPlay, Config
-        sp = SelfPlay(games, Config(**MCTS_CFG), first_game_id=rank * games, device=local_rank, max_children_per_game=24576)
+        cfg = Config(**MCTS_CFG)
+        first = rank * games
+        sp = SelfPlay(games, cfg, first_game_id=first, device=local_rank, max_children_per_game=0)
         sp.run_stub(1)
         sp.reset()
         c0 = sp.counters()
-        ms = sp.run_stub(plies)
+        ms = sp.run_stub(-1)
         c1 = sp.counters()
+        finished = int(sp.env.is_terminal().sum())
+        hists = sp.env.history()
+        pay = sp.env.payoff()
         sp.close()
-        return {"games_per_gpu": games, "plies": plies, "sims": c1["sims"] - c0["sims"], "kernel_ms": ms}
-    except Exception as e:                      # pragma: no cover - informational block only
-        return {"error": str(e)[:200]}
+
+        def pack(hs, py):
+            m = np.zeros((check, 364), dtype=np.int32)
+            for i in range(check):
+                t = [p * 512 + tl for p, tl in hs[i]]
+                m[i, :len(t)] = t
+                m[i, 360:364] = np.round(np.asarray(py[i]) * 12).astype(np.int32)
+            return m
+        owner = 1 if world > 1 else 0
+        mine = pack(hists[:check], pay[:check]) if rank == owner else np.zeros((check, 364), dtype=np.int32)
+        if world > 1:
+            t = torch.from_numpy(mine).cuda()
+            dist.broadcast(t, src=owner)
+            mine = t.cpu().numpy()
+        same = None
+        if rank == 0:
+            sp2 = SelfPlay(check, cfg, first_game_id=owner * games, device=local_rank)
+            sp2.run_stub(-1)
+            same = bool(np.array_equal(pack(sp2.env.history(), sp2.env.payoff()), mine))
+            sp2.close()
+        return {"games": games, "finished": finished, "sims": c1["sims"] - c0["sims"], "kernel_ms": ms,
+                "plies": int(sum(len(h) for h in hists)), "identical": same, "owner": owner, "check": check}
+    except Exception as e:                      # pragma: no cover - informational block only; never fails the bench
+        return {"error": str(e)[:200], "games": games, "finished": 0, "sims": 0, "kernel_ms": 0.0, "plies": 0, "identical": None}
 
 
 def leaf_eval_measure(local_rank: int, rounds: int = 10, warmup: int = 3) -> dict:
@@ -187,18 +245,26 @@ def leaf_eval_measure(local_rank: int, rounds: int = 10, warmup: int = 3) -> dic
     return out
 
 
-def mcts_cpu_baseline(target_seconds: float = 10.0) -> dict:
+def rust_toolchain_probe() -> dict:
+    """if a Rust toolchain ever appears on the box the unmodified `blokus` crate could be the CPU arm.
+    Probed at run time and recorded in the line; absent in every image seen so far."""
+    import shutil
+    return {"rustc": shutil.which("rustc"), "cargo": shutil.which("cargo")}
+
+
+def mcts_cpu_baseline(games: int = 0) -> dict:
+    """The SAME workload as the GPU's configs[2] measurement, on the host: COMPLETE games of the first `games` global
+    ids of the batch (same seed, same config: 800 sims/move, stub evaluator) by the C++ restatement of
+    self_play/src/simulation.rs, one game per thread (the reference's own parallelism: one process per game)."""
     from oracle import oracle as orc
     thr = host_threads()
+    games = games or max(16, thr)
     cfg = orc.make_config(**{**MCTS_CFG, "c_base": 19652.0})
-    plies = 2
-    r = orc.selfplay_batch(cfg, 0, thr, n_threads=thr, max_plies=plies)
-    rate = r["sims"] / max(r["seconds"], 1e-9)
-    plies = int(max(2, min(24, target_seconds * rate / (800.0 * thr))))
-    r = orc.selfplay_batch(cfg, 0, thr, n_threads=thr, max_plies=plies)
+    r = orc.selfplay_batch(cfg, 0, games, n_threads=thr, max_plies=-1)
     return {"value": r["sims"] / r["seconds"], "unit": "sims/s", "cores": thr, "kind": "port",
-            "sample": f"first {plies} plies of {thr} config-3 games (800 sims/move, stub evaluator) by the C++ restatement "
-                      f"of self_play/src/simulation.rs, one game per thread; {r['sims']} sims in {r['seconds']:.2f} s"}
+            "sample": f"COMPLETE games of global ids 0..{games - 1} of the {MCTS_GAMES}-game config-3 batch (800 sims/move, stub "
+                      f"evaluator, same seed) by the C++ restatement of self_play/src/simulation.rs, one game per thread on "
+                      f"{thr} threads; {r['sims']} sims in {r['seconds']:.1f} s"}
 
 
 def run_reference(args) -> int:
@@ -230,7 +296,14 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Rust reference not buildable in this image (no rustc/cargo); this is oracle/ — a C++ restatement "
                 "of the reference algorithm keeping its data structures",
+        "rust_toolchain": rust_toolchain_probe(),
+        "extra": {},
     }
+    if not args.no_mcts:
+        m = mcts_cpu_baseline(args.mcts_cpu_games)
+        line["extra"]["mcts"] = {"metric": "mcts_sims_per_sec_fixed_priors", "value": m["value"], "unit": "sims/s",
+                                 "config": "configs[2] (CPU sample of the same workload)", "cpu_baseline": m,
+                                 "e2e": {"value": m["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -245,6 +318,9 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true", help="skip the secondary MCTS sims/s measurement")
     ap.add_argument("--mcts-plies", type=int, default=-1, help="plies per game in the MCTS measurement (<0: whole games)")
+    ap.add_argument("--mcts-cpu-games", type=int, default=0, help="complete games of the CPU MCTS sample (0: max(16, host threads))")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the extra.env_sustained loop")
+    ap.add_argument("--no-config5", action="store_true", help="skip extra.config5_shard (8192 complete games per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -348,6 +424,33 @@ def main() -> int:
         movegens += c["movegens"]
     barrier()
 
+    # ---- the same step looped for >= 2 s of timed work, clocks sampled INSIDE the loop (sustained clocks) ----
+    n_sus = torch.tensor([max(args.steps, int(args.sustained_seconds * 1e3 / max(region_ms / args.steps, 1e-3)) + 1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(n_sus, op=dist.ReduceOp.MAX)
+    sus_steps = int(n_sus.item())
+    sus_sampler = ClockSampler(local_rank)
+    sus_sampler.start()
+    sus_ms = 0.0
+    sus_kernel_ms = 0.0
+    sus_moves = 0
+    sus_lane_ops = 0
+    for k in range(sus_steps):
+        flush_l2()
+        batch.event_record(0)
+        device_step(5000 + k)
+        batch.event_record(1)
+        sus_ms += batch.event_elapsed_ms()
+        sus_kernel_ms += batch.last_kernel_ms()
+        c = batch.counters()
+        sus_moves += c["total_steps"]
+        sus_lane_ops += c["lane_ops"]
+    sus_clocks = sus_sampler.stop()
+    barrier()
+    burst_clocks = sampler.stop()           # "clocks": every sample taken during the value's steps and the sustained loop
+    sampler = ClockSampler(local_rank)      # the remaining regions (e2e, MCTS, config 5, leaf evaluation)
+    sampler.start()
+
     # ---- end-to-end timed region (host buffers in and out, every step) -----------------------------
     for w in range(args.warmup):
         e2e_step(2000 + w)
@@ -367,9 +470,9 @@ def main() -> int:
         print("e2e per-step us:", [round(1e6 * x) for x in per_step], file=sys.stderr)
     barrier()
 
-    # ---- secondary metric: MCTS sims/s (configs[2]) -------------------------------------------------
+    # ---- secondary metric: MCTS sims/s (configs[2]), configs[4]'s per-GPU share, leaf evaluation ----------------
     mcts = None
-    mcts_big = None
+    c5 = None
     leaf = None
     if not args.no_mcts:
         batch.close()
@@ -379,38 +482,46 @@ def main() -> int:
         barrier()
         mcts = mcts_measure(local_rank, rank, args.mcts_plies)
         barrier()
-        mcts_big = mcts_large_batch_measure(local_rank, rank) if rank == 0 else None
-        barrier()
+        if not args.no_config5:
+            c5 = config5_shard_measure(local_rank, rank, world, dist)
+            barrier()
         leaf = leaf_eval_measure(local_rank) if rank == 0 else None
-    clocks = sampler.stop()     # sampled over every timed region: device-resident steps, e2e steps, MCTS, leaf evaluation
+    clocks = sampler.stop()     # sampled over the e2e steps, MCTS, config-5 shard and leaf evaluation regions
 
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
-    stats = torch.tensor([region_ms, e2e_s, kernel_ms, mcts["kernel_ms"] if mcts else 0.0], dtype=torch.float64, device="cuda")
-    work = torch.tensor([moves, e2e_moves, lane_ops, movegens, mcts["sims"] if mcts else 0,
-                         mcts["plies"] if mcts else 0, mcts["finished_games"] if mcts else 0,
-                         mcts["lane_ops"] if mcts else 0, mcts["entries"] if mcts else 0], dtype=torch.float64, device="cuda")
+    z = lambda d, k: (d[k] if d else 0)
+    stats = torch.tensor([region_ms, e2e_s, kernel_ms, z(mcts, "kernel_ms"), z(mcts, "e2e_s"), z(c5, "kernel_ms"), sus_ms, sus_kernel_ms],
+                         dtype=torch.float64, device="cuda")
+    work = torch.tensor([moves, e2e_moves, lane_ops, movegens, z(mcts, "sims"), z(mcts, "plies"), z(mcts, "finished_games"),
+                         z(mcts, "lane_ops"), z(mcts, "entries"), z(mcts, "e2e_sims"), z(mcts, "e2e_d2h_bytes"), z(c5, "games"),
+                         z(c5, "finished"), z(c5, "sims"), z(c5, "plies"), sus_moves, sus_lane_ops], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    region_ms, e2e_s, kernel_ms, mcts_ms = stats.tolist()
-    moves, e2e_moves, lane_ops, movegens, mcts_sims, mcts_plies, mcts_done, mcts_lane_ops, mcts_entries = work.tolist()
+    region_ms, e2e_s, kernel_ms, mcts_ms, mcts_e2e_s, c5_ms, sus_ms, sus_kernel_ms = stats.tolist()
+    (moves, e2e_moves, lane_ops, movegens, mcts_sims, mcts_plies, mcts_done, mcts_lane_ops, mcts_entries, mcts_e2e_sims, mcts_d2h,
+     c5_games, c5_finished, c5_sims, c5_plies, sus_moves, sus_lane_ops) = work.tolist()
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         value = moves / (region_ms * 1e-3)
-        # roofline of the dominant kernel (k_playout), per launch on one GPU
+        # roofline of the dominant kernel (k_playout), per launch on one GPU.  The roof that binds it is INT32 issue.
         launch_ms = kernel_ms / args.steps
         moves_per_launch = moves / args.steps / world
-        achieved_gbs = ALGO_BYTES_PER_MOVE * moves_per_launch / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_k_playout_dram_bytes.json")
-        if os.path.exists(tpath):
+        lane_ops_per_launch = lane_ops / args.steps / world
+        prof = {}
+        for name in ("r02_k_playout_dram_bytes.json", "r02_int_peak.json"):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                prof[name] = json.load(open(os.path.join(ROOT, "profiles", name)))
             except Exception:
-                traffic = None
-        int_peak = probe_int_peak(local_rank)
-        int_ach = (lane_ops / args.steps / world) / (launch_ms * 1e-3)
+                prof[name] = {}
+        traffic = prof["r02_k_playout_dram_bytes.json"].get("dram_bytes_per_launch")
+        int_peak_live = probe_int_peak(local_rank)
+        int_peak = prof["r02_int_peak.json"].get("lane_ops_per_s") or int_peak_live
+        int_ach = lane_ops_per_launch / (launch_ms * 1e-3)
+        sus_launch_ms = sus_kernel_ms / max(sus_steps, 1)
+        sus_int_ach = (sus_lane_ops / max(sus_steps, 1) / world) / (sus_launch_ms * 1e-3)
+        hbm_algo = ALGO_BYTES_PER_MOVE * moves_per_launch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": region_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -420,33 +531,49 @@ def main() -> int:
                        "games_per_gpu": n, "moves_per_step": moves / args.steps, "seed": SEED,
                        "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": "global game ids, rank r owns [r*n, (r+1)*n); no data-path collective"},
-            # kernels of this library launched inside the timed regions: device-resident steps (k_reset + k_playout) and
-            # end-to-end steps (k_reset + k_playout + k_scores); the MCTS and leaf-evaluation regions add theirs below
-            "gpu_launches": 2 * args.steps + 3 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                         "kernel": "k_playout", "launch_ms": launch_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MOVE * moves_per_launch,
-                         "note": "708 B/move is SURVEY §8d's figure for state round-tripping HBM every move; the "
-                                 "persistent kernel keeps state in registers, so the path is integer-issue bound, "
-                                 "not HBM bound — see int_roofline"},
-            "int_roofline": {"bound": "int32 issue", "achieved": int_ach, "peak": int_peak, "unit": "lane-ops/s",
-                             "frac": int_ach / int_peak, "peak_source": "measured live (bk_probe_int_peak, LOP3/SHF mix)",
-                             "algorithmic_lane_ops_per_launch": lane_ops / args.steps / world,
-                             "note": "algorithmic lane-ops = sum over turn-start move generations of 120*C_rem (SURVEY §8d)"},
+            # kernels of this library launched inside the timed regions: device-resident steps (k_reset + k_playout), the
+            # sustained loop (same two), end-to-end steps (k_reset + k_playout + k_scores); the other regions add theirs below
+            "gpu_launches": 2 * args.steps + 2 * int(sus_steps) + 3 * args.steps,
+            "roofline": {"bound": "int32", "achieved": int_ach, "peak": int_peak, "unit": "lane-ops/s", "frac": int_ach / int_peak,
+                         "traffic": traffic, "kernel": "k_playout", "launch_ms": launch_ms,
+                         "algorithmic_lane_ops_per_launch": lane_ops_per_launch,
+                         "peak_source": ("profiles/r02_int_peak.json (bk_probe_int_peak on this pool's B200, LOP3/SHF mix, clocks recorded beside it)"
+                                         if prof["r02_int_peak.json"] else "measured live (bk_probe_int_peak)") + "; not in MEASURED_PEAKS.json, "
+                                        "nominal 148 SM x 4 x 16 lanes x 1.965 GHz = 1.86e13",
+                         "peak_live": int_peak_live,
+                         "sustained": {"achieved": sus_int_ach, "frac": sus_int_ach / int_peak, "launch_ms": sus_launch_ms,
+                                       "see": "extra.env_sustained"},
+                         "note": "algorithmic lane-ops = sum over turn-start move generations of 120*C_rem (SURVEY §8d), counted "
+                                 "exactly on the device; `traffic` = measured DRAM bytes per launch (ncu --set full, profiles/)"},
+            "hbm_note": {"bound": "hbm", "algorithmic_bytes_per_launch": hbm_algo, "measured_traffic_bytes_per_launch": traffic,
+                         "achieved_measured_gbs": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
+                         "notional_gbs_at_708_B_per_move": hbm_algo / (launch_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                         "peak_source": peak_kind,
+                         "note": "SURVEY §8d's 708 B/move is what a design that round-trips the state through HBM every move would "
+                                 "move; the persistent kernel keeps the state in registers and moves ~0.3 % of that — HBM does not bind"},
             "e2e": {"value": e2e_moves / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
-            "clocks": clocks,
-            "extra": {"movegens_per_move": movegens / max(moves, 1), "kernel_only_moves_per_s": moves / (kernel_ms * 1e-3)},
+            "clocks": burst_clocks,
+            "extra": {"movegens_per_move": movegens / max(moves, 1), "kernel_only_moves_per_s": moves / (kernel_ms * 1e-3),
+                      "env_sustained": {"value": sus_moves / (sus_ms * 1e-3), "unit": UNIT, "steps": int(sus_steps),
+                                        "seconds_of_timed_work": sus_ms * 1e-3, "ms_per_step": sus_ms / max(sus_steps, 1),
+                                        "int32_frac": sus_int_ach / int_peak, "clocks": sus_clocks,
+                                        "what": "the value's step (reset + playout of the batch, L2 flushed before each) repeated until the "
+                                                "CUDA-event time sums to >= 2 s; nvidia-smi sampled every 100 ms inside the loop"},
+                      "clocks_other_regions": clocks},
         }
         if mcts:
-            line["gpu_launches"] += 1
+            line["gpu_launches"] += 2 + 2
             line["extra"]["mcts"] = {
                 "metric": "mcts_sims_per_sec_fixed_priors", "value": mcts_sims / (mcts_ms * 1e-3), "unit": "sims/s",
                 "config": "configs[2]: 1024 games per GPU, 800 sims/move, fixed uniform priors (stub evaluator), Dirichlet "
                           "alpha 0.03 frac 0.25, sample_moves 30; " + ("complete games" if args.mcts_plies < 0 else f"first {args.mcts_plies} plies"),
                 "sims": mcts_sims, "plies_searched": mcts_plies, "finished_games": mcts_done, "kernel_ms": mcts_ms,
                 "kernel": "k_selfplay_stub (one launch: every ply's root expansion, noise, 800 sims, action, apply)",
+                "e2e": {"value": mcts_e2e_sims / mcts_e2e_s, "unit": "sims/s", "seconds": mcts_e2e_s,
+                        "h2d_bytes_per_step": mcts["e2e_h2d_bytes"], "d2h_bytes_per_step": mcts_d2h / world,
+                        "what": "bk_selfplay_reset + bk_selfplay_run_stub + the finished-game training tuples (packed policy records, "
+                                "packed histories, plies, scores, payoffs) copied into host memory, host-timed, max over ranks"},
                 # ~1.6 KB algorithmic HBM bytes per simulation
                 "roofline": {"bound": "hbm", "achieved": 1600.0 * mcts_sims / world / (mcts_ms * 1e-3) / 1e9,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -455,22 +582,26 @@ def main() -> int:
                                  "frac": mcts_lane_ops / world / (mcts_ms * 1e-3) / int_peak},
                 "child_entries_created": mcts_entries,
             }
-        if mcts_big and "error" not in mcts_big:
+        if c5:
             line["gpu_launches"] += 1
-            line["extra"]["mcts_large_batch"] = {
-                "metric": "mcts_sims_per_sec_fixed_priors", "value": mcts_big["sims"] / (mcts_big["kernel_ms"] * 1e-3), "unit": "sims/s",
-                "config": f"configs[4] per-GPU shape on rank 0: {mcts_big['games_per_gpu']} games, 800 sims/move, stub evaluator, "
-                          f"first {mcts_big['plies']} plies (k_selfplay_stub<20>: 20 resident games per SM)",
-                "sims": mcts_big["sims"], "kernel_ms": mcts_big["kernel_ms"]}
-        elif mcts_big:
-            line["extra"]["mcts_large_batch"] = mcts_big
+            line["extra"]["config5_shard"] = {
+                "config": f"configs[4] per-GPU share: {int(c5['games'])} complete self-play games per GPU ({int(c5_games)} on {world} GPU"
+                          f"{'s' if world > 1 else ''}, global game ids), 800 sims/move, stub evaluator, one launch per GPU",
+                "games": int(c5_games), "finished_games": int(c5_finished), "sims": c5_sims, "plies": c5_plies,
+                "seconds_max_over_ranks": c5_ms * 1e-3, "games_per_s": c5_games / max(c5_ms * 1e-3, 1e-9),
+                "sims_per_s": c5_sims / max(c5_ms * 1e-3, 1e-9),
+                "cross_check": {"identical": c5.get("identical"), "ids": [c5["owner"] * c5["games"], c5["owner"] * c5["games"] + c5["check"] - 1],
+                                "owner_rank": c5["owner"], "replayed_on_rank": 0,
+                                "what": "action traces and payoffs of the slice replayed on rank 0 as a separate small batch"} if "owner" in c5 else None,
+                "error": c5.get("error")}
         if leaf:
             flops = 18883996800.0 * MCTS_GAMES
-            line["gpu_launches"] += 41 * 10          # 41 hand-written convolutions per round, 10 timed rounds
+            line["gpu_launches"] += 43 * 10          # pack + 41 convolutions + heads per round, 10 timed rounds
             line["extra"]["leaf_eval"] = {
                 "metric": "resnet20x256_leaf_evals_per_sec", "value": MCTS_GAMES / (leaf["tcgen05"] * 1e-3), "unit": "leaves/s",
                 "config": "configs[3] building block: ResNet(20,256) random init, eval mode, 1024 leaves per round, one GPU; "
-                          "hand-written tcgen05/TMEM/TMA convolutions (bk_conv3x3_bf16), bf16 operands, f32 accumulate",
+                          "native evaluator (bk_evaluator_forward): plane packing, 41 hand-written tcgen05/TMEM/TMA convolutions "
+                          "(bf16 operands, f32 accumulate), fused head kernel — no PyTorch ops in the round",
                 "ms_per_round": leaf["tcgen05"], "cudnn_bf16_ms_per_round": leaf["cudnn_bf16"],
                 "speedup_vs_cudnn_bf16": leaf["cudnn_bf16"] / leaf["tcgen05"],
                 "roofline": {"bound": "tensor", "achieved": flops / (leaf["tcgen05"] * 1e-3) / 1e12,
@@ -481,7 +612,8 @@ def main() -> int:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             if mcts:
-                line["extra"]["mcts"]["cpu_baseline"] = mcts_cpu_baseline()
+                line["extra"]["mcts"]["cpu_baseline"] = mcts_cpu_baseline(args.mcts_cpu_games)
+        line["rust_toolchain"] = rust_toolchain_probe()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(device_ids=[local_rank])
