@@ -9,6 +9,7 @@
 
 #include "bk_host.h"
 #include "bk_mcts_kernels.cuh"
+#include "bk_mcts_pipe.cuh"
 #include "bk_eval_kernels.cuh"
 
 struct bk_selfplay {
@@ -30,6 +31,7 @@ struct bk_selfplay {
     bool use_vl = false;
     int num_sms = 148;
     int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
+    int stub_pipe = -1;               // -1 = two-warp pipeline for small exact-mode batches; BK_STUB_PIPE=0/1 forces it off/on
     uint32_t* d_pol_off = nullptr;    // [n][BK_HIST_CAP + 1]
     uint16_t* d_pol_tile = nullptr;   // [n][policy_cap]
     uint32_t* d_pol_visits = nullptr; // [n][policy_cap]
@@ -91,6 +93,27 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
     kb_selfplay_stub(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
                      pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies,
                      counters, g, lane, tabs, wsm);
+}
+
+// Exact mode, small batches: two warps per game — warp 0 selects and backs up one simulation ahead of warp 1, which applies,
+// generates moves and expands (bk_mcts_pipe.cuh).  Same results as k_selfplay_stub bit for bit.
+// 7 resident games per SM (1024 games on 148 SMs are 6.9 per SM): 144 registers per thread.  With the 195 the compiler would
+// like, only 5 CTAs fit an SM and 1024 games run in two waves (measured: 1.55 s against 1.26 s for the one-warp kernel).
+__global__ void __launch_bounds__(64, 7)
+k_selfplay_stub_pipe(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies, unsigned long long* counters) {
+    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ BkWarpSmem wsm;
+    __shared__ BkPathBuf pbs[2];
+    __shared__ BkPipeShared ps;
+    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const BkTree tr = bk_tree_of(pl, cfg, g);
+    kb_selfplay_stub_pipe(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+                          pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies, counters, g,
+                          warp, lane, tabs, wsm, pbs, ps);
 }
 
 __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl, const BkState* states, int n) {
@@ -337,6 +360,7 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
         if (const char* e = getenv("BK_STUB_MIN_BLOCKS")) sp->stub_min_blocks = atoi(e);
     }
 #endif
+    if (const char* e = getenv("BK_STUB_PIPE")) sp->stub_pipe = atoi(e);     // probes / tests: 0 = one-warp kernel, 1 = pipeline
     int rc = bk_env_create(n_games, device, &sp->env);
     if (rc) { delete sp; return rc; }
     rc = selfplay_alloc(sp, cfg, first_game_id, max_children_per_game);
@@ -476,7 +500,12 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     BK_CUDA(cudaEventRecord(sp->ev0, st));
     const int per_sm = (sp->n + sp->num_sms - 1) / sp->num_sms;     // games an SM would hold if all were resident
     const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= 9 ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : 20)));
-    if (minb >= 20)
+    // exact mode and a batch small enough to be latency bound (<= 9 games per SM): the two-warp pipeline
+    const bool pipe = sp->dcfg.mode == 0u && (sp->stub_pipe > 0 || (sp->stub_pipe < 0 && per_sm <= 9 && !sp->stub_min_blocks));
+    if (pipe)
+        BK_LAUNCH(k_selfplay_stub_pipe, sp->n, 64, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n, max_plies,
+                  sp->d_counters);
+    else if (minb >= 20)
         BK_LAUNCH(k_selfplay_stub<20>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
                   max_plies, sp->d_counters);
     else if (minb >= 16)

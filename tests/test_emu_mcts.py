@@ -1,4 +1,6 @@
 """MCTS kernel-source logic checks on the CPU warp emulator (small trees; the GPU tests go to 800 sims)."""
+import numpy as np
+
 import parity
 
 
@@ -118,3 +120,38 @@ def test_emu_dense_rows_across_scan_chunks(emu_lib, orc):
             assert np.array_equal(roots[0][key], roots[g][key]), (g, key)
     assert int(roots[0]["visits"].sum()) == 2
     a.close()
+
+
+def _pipeline_equals_one_warp_kernel(lib, n_games, sims, max_plies):
+    """The two-warp pipelined stub kernel (bk_mcts_pipe.cuh) against the one-warp kernel: histories, every policy record,
+    the last root's value sums and priors, and the counters — complete games, so terminal leaves (remembered in the
+    entry, speculation rolled back on first discovery) are covered."""
+    import os
+    from blokus_self_play import SelfPlay, Config
+    cfg = Config(sims_per_move=sims, sample_moves=8, c_base=19652, c_init=1.25, dirichlet_alpha=0.3, exploration_fraction=0.25, seed=12)
+    out = []
+    for pipe in ("0", "1"):
+        os.environ["BK_STUB_PIPE"] = pipe
+        try:
+            sp = SelfPlay(n_games, cfg, first_game_id=70, lib=lib)
+        finally:
+            del os.environ["BK_STUB_PIPE"]
+        sp.run_stub(max_plies)
+        out.append((sp.env.history(), sp.policy_records(), sp.last_root(), sp.counters(), sp.env.payoff().tolist()))
+        sp.close()
+    (h0, r0, l0, c0, p0), (h1, r1, l1, c1, p1) = out
+    assert h0 == h1 and p0 == p1
+    for ga, gb in zip(r0, r1):
+        assert len(ga) == len(gb)
+        for (t1, v1), (t2, v2) in zip(ga, gb):
+            assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+    for a, b in zip(l0, l1):
+        assert np.array_equal(a["value_sum"], b["value_sum"]) and np.array_equal(a["prior"], b["prior"])
+    assert c0["sims"] == c1["sims"] and c0["nodes"] == c1["nodes"] and c0["entries"] == c1["entries"]
+    assert c1["applies"] <= c0["applies"]              # revisited terminal leaves are not re-applied by the pipeline
+    return h1
+
+
+def test_emu_pipeline_equals_one_warp_kernel(emu_lib):
+    h = _pipeline_equals_one_warp_kernel(emu_lib, 2, 10, -1)
+    assert all(len(x) > 200 for x in h)

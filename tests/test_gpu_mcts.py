@@ -226,3 +226,10 @@ def test_gpu_dense_rows_many_games(cuda_lib, orc):
         for (t1, v1), (t2, v2) in zip(recs[0], recs[g]):
             assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
     sp.close()
+
+
+def test_gpu_pipeline_equals_one_warp_kernel(cuda_lib):
+    """Two-warp pipelined stub kernel == one-warp kernel, complete games at 200 sims (terminal leaves inside the trees)."""
+    from test_emu_mcts import _pipeline_equals_one_warp_kernel
+    h = _pipeline_equals_one_warp_kernel(cuda_lib, 24, 200, -1)
+    assert all(len(x) > 200 for x in h)
