@@ -125,6 +125,8 @@ _SIGNATURES = {
     "bk_selfplay_training_sizes": (C.c_int, [_P, _P, _P]),
     "bk_selfplay_training_tensors": (C.c_int, [_P, _P, _P, _P]),
     "bk_selfplay_counters": (C.c_int, [_P, _P]),
+    "bk_selfplay_counters_raw": (C.c_int, [_P, _P]),
+    "bk_selfplay_probe_stats": (C.c_int, [_P, _P]),
     "bk_selfplay_last_kernel_ms": (C.c_int, [_P, _P]),
 }
 

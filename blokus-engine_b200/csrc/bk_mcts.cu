@@ -1,6 +1,7 @@
 // bk_mcts.cu — MCTS self-play clients: kernel wrappers and the bk_selfplay_* C ABI
 // (include/blokus_b200.h).  Host mirror of self_play/src/lib.rs:9-32 + simulation.rs:267-296, batched.
 #include <math.h>
+#include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -36,8 +37,10 @@ struct bk_selfplay {
     uint16_t* d_pol_tile = nullptr;   // [n][policy_cap]
     uint32_t* d_pol_visits = nullptr; // [n][policy_cap]
     float* d_ucb = nullptr;
+    float* d_rcp = nullptr;           // RN(1/d) table of bk_ucb_div
+    bool short_div = false;           // the short division was verified exhaustively for this configuration
     float* d_prior = nullptr;
-    unsigned long long* d_counters = nullptr;  // [8], cumulative
+    unsigned long long* d_counters = nullptr;  // [16], cumulative ([6..] are used by probe builds only)
     uint8_t* d_stage = nullptr;       // [n][400 * 16] gather staging for last_root
     int32_t* d_round = nullptr;       // [4] per-round scalars of the fused network loop
     int64_t* d_ply_off = nullptr;     // [n + 1] prefix of plies per game (training tensors)
@@ -395,14 +398,14 @@ static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_
     BK_CUDA(cudaMalloc(&sp->d_pol_off, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_pol_tile, sizeof(uint16_t) * size_t(d.policy_cap) * size_t(n_games)));
     BK_CUDA(cudaMalloc(&sp->d_pol_visits, sizeof(uint32_t) * size_t(d.policy_cap) * size_t(n_games)));
-    BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 8));
+    BK_CUDA(cudaMalloc(&sp->d_counters, sizeof(unsigned long long) * 16));
     BK_CUDA(cudaMalloc(&sp->d_stage, size_t(n_games) * 400 * 16));
     BK_CUDA(cudaMalloc(&sp->d_round, sizeof(int32_t) * 4));
     BK_CUDA(cudaMalloc(&sp->d_slot_base, sizeof(uint32_t) * (size_t(n_games) + 1)));
     BK_CUDA(cudaMemsetAsync(sp->d_slot_base, 0, sizeof(uint32_t) * (size_t(n_games) + 1), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_hdr, 0, sizeof(BkSearchHdr) * size_t(n_games), sp->env->stream));
     BK_CUDA(cudaMemsetAsync(sp->d_pol_off, 0, sizeof(uint32_t) * (BK_HIST_CAP + 1) * size_t(n_games), sp->env->stream));
-    BK_CUDA(cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned long long) * 8, sp->env->stream));
+    BK_CUDA(cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned long long) * 16, sp->env->stream));
     // simulation.rs:91-93 — the factor of ucb_score that depends only on the parent's visit count,
     // evaluated on the host with the platform libm exactly as the reference's f32 expression reads
     std::vector<float> ucb(size_t(cfg->sims_per_move) + 2);
@@ -415,6 +418,23 @@ static int selfplay_alloc(bk_selfplay* sp, const bk_config* cfg, uint32_t first_
     const float e1 = host_exp_f32(1.0f);
     float total = 0.0f;
     for (int k = 1; k <= 400; ++k) { total += e1; prior[size_t(k)] = e1 / total; }
+    // bk_ucb_div: exhaustive check of the short division over every (parent visits, child visits) pair this handle can see
+    std::vector<float> rcp(ucb.size() + 1, 0.0f);
+    for (size_t d = 1; d < rcp.size(); ++d) rcp[d] = 1.0f / float(d);
+    bool short_div_exact = getenv("BK_NO_SHORT_DIV") == nullptr && cfg->sims_per_move <= 4096u;   // (sims + 2)^2 checks: bounded
+    for (size_t i = 0; i < ucb.size() && short_div_exact; ++i)
+        for (size_t d = 1; d < rcp.size(); ++d) {
+            const float F = ucb[i], fd = float(d), q0 = F * rcp[d];
+            const float q = std::fmaf(std::fmaf(-fd, q0, F), rcp[d], q0);
+            const float want = F / fd;
+            uint32_t a, b;
+            memcpy(&a, &q, 4); memcpy(&b, &want, 4);
+            if (a != b) { short_div_exact = false; break; }
+        }
+    sp->short_div = short_div_exact;
+    BK_CUDA(cudaMalloc(&sp->d_rcp, sizeof(float) * rcp.size()));
+    BK_CUDA(cudaMemcpy(sp->d_rcp, rcp.data(), sizeof(float) * rcp.size(), cudaMemcpyHostToDevice));
+    d.rcp_tab = short_div_exact ? sp->d_rcp : nullptr;
     BK_CUDA(cudaMalloc(&sp->d_ucb, sizeof(float) * ucb.size()));
     BK_CUDA(cudaMalloc(&sp->d_prior, sizeof(float) * prior.size()));
     BK_CUDA(cudaMemcpy(sp->d_ucb, ucb.data(), sizeof(float) * ucb.size(), cudaMemcpyHostToDevice));
@@ -434,7 +454,7 @@ void bk_selfplay_destroy(bk_selfplay* sp) {
     cudaSetDevice(sp->device);
     cudaFree(sp->d_S); cudaFree(sp->d_X); cudaFree(sp->d_nodes);
     cudaFree(sp->d_scratch); cudaFree(sp->d_hdr); cudaFree(sp->d_pol_off); cudaFree(sp->d_pol_tile);
-    cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
+    cudaFree(sp->d_pol_visits); cudaFree(sp->d_ucb); cudaFree(sp->d_rcp); cudaFree(sp->d_prior); cudaFree(sp->d_counters);
     cudaFree(sp->d_stage);
     cudaFree(sp->d_round);
     cudaFree(sp->d_ply_off);
@@ -843,6 +863,33 @@ int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]) {
     BK_CUDA(cudaMemcpyAsync(h, sp->d_counters, sizeof h, cudaMemcpyDeviceToHost, sp->env->stream));
     BK_CUDA(cudaStreamSynchronize(sp->env->stream));
     for (int i = 0; i < 6; ++i) out[i] = h[i];
+    return BK_OK;
+}
+
+int bk_selfplay_counters_raw(bk_selfplay* sp, uint64_t out[16]) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    unsigned long long h[16];
+    BK_CUDA(cudaMemcpyAsync(h, sp->d_counters, sizeof h, cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    for (int i = 0; i < 16; ++i) out[i] = h[i];
+#if defined(BK_PIPE_STATS) && !defined(BK_WARP_EMU)
+    unsigned long long g[32];
+    BK_CUDA(cudaMemcpyFromSymbol(g, g_pipe_stats, sizeof g));
+    for (int i = 0; i < 7; ++i) out[9 + i] = g[i];
+#endif
+    return BK_OK;
+}
+
+int bk_selfplay_probe_stats(bk_selfplay* sp, uint64_t out[32]) {
+    int rc = sp_use(sp);
+    if (rc) return rc;
+    for (int i = 0; i < 32; ++i) out[i] = 0;
+#if defined(BK_PIPE_STATS) && !defined(BK_WARP_EMU)
+    unsigned long long g[32];
+    BK_CUDA(cudaMemcpyFromSymbol(g, g_pipe_stats, sizeof g));
+    for (int i = 0; i < 32; ++i) out[i] = g[i];
+#endif
     return BK_OK;
 }
 

@@ -51,6 +51,7 @@ struct BkSearchCfg {
     uint32_t max_nodes, entry_cap, policy_cap;
     uint32_t mode, leaves_per_round;
     const float* ucb_tab;    // [sims + 2]: (ln((N + c_base + 1)/c_base) + c_init) * sqrt(N), host libm
+    const float* rcp_tab;    // [sims + 2]: RN(1/d), or NULL — see bk_ucb_div
     const float* prior_tab;  // [401]: stub prior for n children = e / (e + e + ... n times), f32 sequential
     float stub_value;        // 0.25
 };
@@ -115,6 +116,22 @@ __device__ __forceinline__ void bk_store_stream(BkState* __restrict__ s, int lan
         BK_ST_STREAM(reinterpret_cast<uint4*>(&s->alive), make_uint4(G.alive, G.tw0, G.tw1, G.tw2));
     }
     BK_ST_STREAM(&s->smask[lane], (unsigned short)(G.smask));
+}
+
+// simulation.rs:92-94: u = F / (1 + N), an IEEE f32 division on the select's critical path (one per child per level).
+// N + 1 = d is a small integer and F is one of the sims + 2 values of ucb_tab, so there are only (sims + 2)^2 possible
+// divisions: the host checks ALL of them (bk_selfplay_create) against the three-operation form
+//     q0 = RN(F * r), r = RN(1/d);   rem = fma(-d, q0, F) (exact);   q = fma(rem, r, q0)
+// and passes rcp_tab only if every quotient equals RN(F / d) bit for bit; otherwise rcp_tab is NULL and the IEEE
+// division is used.  Same result, a third of the latency (no MUFU.RCP + Newton + range fix-up).
+__device__ __forceinline__ float bk_ucb_div(const BkSearchCfg& cfg, float F, uint32_t n_visits) {
+    if (cfg.rcp_tab) {
+        const float r = cfg.rcp_tab[n_visits + 1u];
+        const float d = float(n_visits + 1u);
+        const float q0 = __fmul_rn(F, r);
+        return __fmaf_rn(__fmaf_rn(-d, q0, F), r, q0);
+    }
+    return __fdiv_rn(F, __fadd_rn(1.0f, float(n_visits)));
 }
 
 // f32 exp as the oracle defines it: exp in f64, rounded once to f32 (see oracle/mcts_oracle.hpp exp_f32)
@@ -323,7 +340,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
                 const uint4 sv = tr.S[off + lane];
                 const uint4 xv = tr.X[off + lane];
                 bk_prefetch_block(tr, sv.w, xv.y);
-                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));                         // simulation.rs:92-94
+                const float u = bk_ucb_div(cfg, F, sv.x);                         // simulation.rs:92-94
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));  // :95-97, Q cached
                 if (sc >= 0.0f) key = __float_as_uint(sc) + 1u;                                     // NaN / negative never wins
                 b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z;
@@ -337,7 +354,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
             for (int i = lane; i < n; i += 32) {
                 const uint4 sv = tr.S[off + i];
                 const uint4 xv = tr.X[off + i];
-                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));
+                const float u = bk_ucb_div(cfg, F, sv.x);
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
                 if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z; }
             }

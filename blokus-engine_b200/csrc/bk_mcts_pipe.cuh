@@ -25,6 +25,24 @@
 
 #define BK_TN_TERMINAL(tn) (((tn) >> 22) & 1u)
 
+// -DBK_PIPE_STATS (probe builds only, tools/probe_mcts_pipe.py): cycles each warp spends waiting for the other go to
+// counters[6] (A) / [7] (B), a game's total cycles to [8]; finer sums over all games to g_pipe_stats:
+// 0 select cycles, 1 levels walked, 2 backup cycles, 3 B: state load + apply, 4 B: expansion + link, 5 selects, 6 voided selects
+#if defined(BK_PIPE_STATS) && !defined(BK_WARP_EMU)
+#define BK_PIPE_T0() const long long _t0 = clock64()
+#define BK_PIPE_T1(acc) (acc) += (unsigned long long)(clock64() - _t0)
+static __device__ unsigned long long g_pipe_stats[32];
+#define BK_STAT_T0(name) const long long name = clock64()
+#define BK_STAT_T1(name, slot) do { if (lane == 0) atomicAdd(&g_pipe_stats[slot], (unsigned long long)(clock64() - name)); } while (0)
+#define BK_STAT_ADD(slot, v) do { if (lane == 0) atomicAdd(&g_pipe_stats[slot], (unsigned long long)(v)); } while (0)
+#else
+#define BK_PIPE_T0() do {} while (0)
+#define BK_PIPE_T1(acc) do {} while (0)
+#define BK_STAT_T0(name) do {} while (0)
+#define BK_STAT_T1(name, slot) do {} while (0)
+#define BK_STAT_ADD(slot, v) do {} while (0)
+#endif
+
 struct BkPathBuf {
     uint32_t e[BK_PATH_CAP];
     uint32_t n[BK_PATH_CAP];      // visits / value sum as the select read them (the backup's inputs, and the rollback's)
@@ -84,7 +102,6 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
     uint32_t node = 0u, off = root.off, Np = root_visits, e = 0u, tn = 0u, mask = 0u;
     int n = int(root.n), depth = 0, kind = BK_SEL_LEAF;
     for (;;) {
-        bk_prefetch_state(&tr.nodes[node], lane);
         const float F = cfg.ucb_tab[Np];
         uint32_t wi, b_tn = 0u, b_n = 0u, b_w = 0u, b_off = 0u, b_node = 0u;
         if (n <= 32) {
@@ -92,7 +109,7 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
             if (lane < n) {
                 const uint4 sv = tr.S[off + lane];
                 const uint4 xv = tr.X[off + lane];
-                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));
+                const float u = bk_ucb_div(cfg, F, sv.x);
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
                 if (sc >= 0.0f) key = __float_as_uint(sc) + 1u;
                 b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z;
@@ -106,7 +123,7 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
             for (int i = lane; i < n; i += 32) {
                 const uint4 sv = tr.S[off + i];
                 const uint4 xv = tr.X[off + i];
-                const float u = __fdiv_rn(F, __fadd_rn(1.0f, float(sv.x)));
+                const float u = bk_ucb_div(cfg, F, sv.x);
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
                 if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z; }
             }
@@ -158,25 +175,34 @@ __device__ __forceinline__ void bk_pipe_backup(const BkTree& tr, int depth, cons
 
 // ---- warp B: the leaf half of a simulation --------------------------------------------------------------------------------
 __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, const BkTree& tr, BkPipeShared& ps, int lane,
-                                                    const BkTabs& tabs, BkWarpSmem& sm, BkCounters& gctr, BkSpCounters& ctr) {
+                                                    const BkTabs& tabs, BkWarpSmem& sm, BkCounters& gctr, BkSpCounters& ctr,
+                                                    unsigned long long& waited) {
     BkSearchHdr hd;
     hd.n_nodes = ps.n_nodes; hd.n_entries = ps.n_entries; hd.err = 0u;
     uint32_t seq = 0u;
     for (;;) {
         uint32_t have;
-        for (;;) {
-            have = bk_pipe_read(&ps.req_seq, lane);
-            if (have != seq) break;
-            if (bk_pipe_read(&ps.quit, lane)) break;
+        {
+            BK_PIPE_T0();
+            for (;;) {
+                have = bk_pipe_read(&ps.req_seq, lane);
+                if (have != seq) break;
+                if (bk_pipe_read(&ps.quit, lane)) break;
+            }
+            BK_PIPE_T1(waited);
         }
         if (have == seq) break;                                     // quit, nothing outstanding
         __threadfence_block();
         const uint32_t parent = ps.req_parent, entry = ps.req_entry;
         const int tile = int(ps.req_tile);
         BkRegs L;
+        BK_STAT_T0(tb0);
         bk_load(&tr.nodes[parent], lane, L);
         uint32_t kind = BK_PIPE_OK, mask = 0u;
-        if (!bk_apply(L, tile, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; kind = BK_PIPE_ERROR; }
+        const bool applied = bk_apply(L, tile, -1, lane, tabs, gctr);
+        BK_STAT_T1(tb0, 3);
+        BK_STAT_T0(tb1);
+        if (!applied) { hd.err |= BK_SP_ERR_APPLY; kind = BK_PIPE_ERROR; }
         else {
             if (lane == 0) ctr.applies += 1u;
             if (bk_terminal(L)) {                                   // simulation.rs:45-47; remembered in the entry
@@ -191,6 +217,7 @@ __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, cons
             }
         }
         __syncwarp();
+        BK_STAT_T1(tb1, 4);
         __threadfence_block();                                      // the tree writes above are visible before the verdict
         seq += 1u;
         if (lane == 0) { ps.res_kind = kind; ps.res_mask = mask; if (hd.err) ps.err = ps.err | hd.err; __threadfence_block(); ps.done_seq = seq; }
@@ -208,15 +235,17 @@ __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, cons
 }
 
 // ---- warp A: select + backup, one simulation ahead of B -----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bk_pipe_wait(BkPipeShared& ps, uint32_t seq, int lane) {
+__device__ __forceinline__ uint32_t bk_pipe_wait(BkPipeShared& ps, uint32_t seq, int lane, unsigned long long& waited) {
+    BK_PIPE_T0();
     while (bk_pipe_read(&ps.done_seq, lane) != seq) {}
+    BK_PIPE_T1(waited);
     __threadfence_block();
     return bk_pipe_read(&ps.res_kind, lane);
 }
 
 // runs cfg.sims simulations of one ply; returns the error flags raised on this side
 __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const BkTree& tr, const BkBlock& root, BkPipeShared& ps,
-                                                   int lane, BkPathBuf (&pbs)[2], BkSpCounters& ctr) {
+                                                   int lane, BkPathBuf (&pbs)[2], BkSpCounters& ctr, unsigned long long& waited) {
     uint32_t err = 0u, started = 0u, seq = 0u, pending = BK_NODE_NONE;
     int cur = 0, pend_depth = 0;
     bool inflight = false;
@@ -233,21 +262,26 @@ __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const
     };
     for (;;) {
         if (started == cfg.sims) {
-            if (inflight) { const uint32_t k = bk_pipe_wait(ps, seq, lane); settle(k); if (k == BK_PIPE_ERROR) err |= BK_SP_ERR_ENTRY_CAP; }
+            if (inflight) { const uint32_t k = bk_pipe_wait(ps, seq, lane, waited); settle(k); if (k == BK_PIPE_ERROR) err |= BK_SP_ERR_ENTRY_CAP; }
             break;
         }
+        BK_STAT_T0(ts0);
         const BkPipeLeaf lf = bk_pipe_select(tr, cfg, root, started + 1u, pending, lane, pbs[cur], err);   // root visits: :194
+        BK_STAT_T1(ts0, 0);
+        BK_STAT_ADD(1, lf.depth);
+        BK_STAT_ADD(5, 1);
         if (lf.kind == BK_SEL_HIT_PENDING) {                        // walked into B's leaf: wait for it, select again
-            const uint32_t k = bk_pipe_wait(ps, seq, lane);
+            const uint32_t k = bk_pipe_wait(ps, seq, lane, waited);
             settle(k);
             if (k == BK_PIPE_ERROR) { err |= BK_SP_ERR_ENTRY_CAP; break; }
+            BK_STAT_ADD(6, 1);
             continue;
         }
         if (inflight) {
-            const uint32_t k = bk_pipe_wait(ps, seq, lane);
+            const uint32_t k = bk_pipe_wait(ps, seq, lane, waited);
             settle(k);
             if (k == BK_PIPE_ERROR) { err |= BK_SP_ERR_ENTRY_CAP; break; }
-            if (k == BK_PIPE_TERMINAL) continue;                    // the select above saw a backup that never happened
+            if (k == BK_PIPE_TERMINAL) { BK_STAT_ADD(6, 1); continue; }   // the select above saw a backup that never happened
         }
         if (lf.kind == BK_SEL_ERROR) break;
         if (lf.kind == BK_SEL_KNOWN_TERMINAL) {                     // payoff already known: no work for B
@@ -266,7 +300,9 @@ __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const
         inflight = true;
         pending = lf.entry;
         pend_depth = lf.depth;
+        BK_STAT_T0(tk0);
         bk_pipe_backup(tr, lf.depth, stub, 0, lane, pbs[cur]);      // speculative: right unless the leaf is terminal
+        BK_STAT_T1(tk0, 2);
         started += 1u;
         cur ^= 1;
     }
@@ -286,10 +322,12 @@ __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, Bk
     BkSearchHdr hd;
     BkCounters gctr = {0u, 0u};
     BkSpCounters ctr = {0u, 0u, 0u, 0u};
+    unsigned long long waited = 0ull;
     const uint32_t game_id = cfg.first_game_id + uint32_t(g);
     int plies = 0;
     BkBlock root;
     root.off = 0u; root.n = 0u;
+    BK_PIPE_T0();
     if (warp == 0) {
         bk_load(&states[g], lane, G);
         hd.err = hdr_g->err; hd.pol_count = hdr_g->pol_count; hd.plies_searched = hdr_g->plies_searched;
@@ -316,9 +354,9 @@ __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, Bk
         __syncthreads();
         if (!ps.go) break;
         if (warp == 0) {
-            hd.err |= bk_pipe_search(cfg, tr, root, ps, lane, pbs, ctr);
+            hd.err |= bk_pipe_search(cfg, tr, root, ps, lane, pbs, ctr, waited);
         } else {
-            bk_pipe_leaf_worker(cfg, tr, ps, lane, tabs, sm, gctr, ctr);
+            bk_pipe_leaf_worker(cfg, tr, ps, lane, tabs, sm, gctr, ctr, waited);
         }
         __syncthreads();
         if (warp == 0) {
@@ -352,5 +390,11 @@ __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, Bk
         atomicAdd(&counters[3], 120ull * (unsigned long long)crem);
         atomicAdd(&counters[4], (unsigned long long)ctr.entries);
         atomicAdd(&counters[5], (unsigned long long)ctr.nodes);
+#if defined(BK_PIPE_STATS) && !defined(BK_WARP_EMU)
+        unsigned long long total = 0ull;
+        BK_PIPE_T1(total);
+        atomicAdd(&counters[6 + warp], waited);
+        if (warp == 0) atomicAdd(&counters[8], total);
+#endif
     }
 }

@@ -283,6 +283,11 @@ int bk_selfplay_training_tensors(bk_selfplay* sp, float* dev_states, float* dev_
 /* Counters since creation: [0] simulations, [1] Game::apply calls, [2] turn-start move generations,
  * [3] sum of 120*C_rem, [4] child entries created, [5] nodes expanded. */
 int bk_selfplay_counters(bk_selfplay* sp, uint64_t out[6]);
+/* All 16 counter slots; [6..] are written only by instrumented probe builds (-DBK_PIPE_STATS: cycles the two warps of the
+ * pipelined stub kernel spend waiting for each other, and total cycles). */
+int bk_selfplay_counters_raw(bk_selfplay* sp, uint64_t out[16]);
+/* Finer probe counters of instrumented builds (zeros otherwise); layout documented in csrc/bk_mcts_pipe.cuh. */
+int bk_selfplay_probe_stats(bk_selfplay* sp, uint64_t out[32]);
 int bk_selfplay_last_kernel_ms(bk_selfplay* sp, float* ms_out);
 
 /* ---- leaf evaluator building block ------------------------------------------------ */

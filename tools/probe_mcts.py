@@ -8,7 +8,7 @@ CASES = [(8192, 12)] if os.environ.get('BK_BIG') else [(1024, -1)] if os.environ
 cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
              exploration_fraction=0.25, seed=1)
 for n, plies in CASES:
-    sp = SelfPlay(n, cfg, lib=LIB)
+    sp = SelfPlay(n, cfg, lib=LIB, max_children_per_game=int(os.environ.get('BK_CAP', '0')))
     c0 = sp.counters()
     t = time.time()
     ms = sp.run_stub(plies)
