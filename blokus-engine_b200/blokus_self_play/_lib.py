@@ -71,6 +71,7 @@ _SIGNATURES = {
     "bk_env_place_piece": (C.c_int, [_P, _P, _P, _P, _P]),
     "bk_env_legal_mask": (C.c_int, [_P, _P]),
     "bk_env_legal_rows": (C.c_int, [_P, _P]),
+    "bk_env_legal_tiles": (C.c_int, [_P, _P, _P]),
     "bk_env_board": (C.c_int, [_P, _P]),
     "bk_env_anchors": (C.c_int, [_P, C.c_int, _P]),
     "bk_env_current_player": (C.c_int, [_P, _P]),

@@ -90,9 +90,11 @@ class GameBatch:
         return self._get(self.lib.bk_env_legal_rows, (self.n, 20), np.uint32)
 
     def legal_tiles(self):
-        """Game::get_legal_tiles per game, ascending."""
-        m = self.legal_mask()
-        return [np.flatnonzero(m[g]).tolist() for g in range(self.n)]
+        """Game::get_legal_tiles per game (game.rs:242-244), ascending: the list form of the C ABI."""
+        counts = np.zeros(self.n, dtype=np.int32)
+        tiles = np.zeros((self.n, 400), dtype=np.int16)
+        self.lib.check(self.lib.bk_env_legal_tiles(self._h, _ptr(counts), _ptr(tiles)))
+        return [tiles[g, : counts[g]].astype(int).tolist() for g in range(self.n)]
 
     def board(self) -> np.ndarray:
         return self._get(self.lib.bk_env_board, (self.n, 400), np.uint8)

@@ -270,18 +270,31 @@ class SelfPlay:
 
     def game_data(self) -> List[Tuple[list, list, list]]:
         """What training_game() returns for each game (simulation.rs:293-295):
-        (history [(player, tile)], policies [[(tile, prob)]], values [4])."""
+        (history [(player, tile)], policies [[(tile, prob)]], values [4]).
+        The probabilities of every ply of every game are computed in one vectorised pass over the packed gather
+        (f32 visits / f32 total, simulation.rs:222); only the final nesting into the reference's list-of-tuples is Python."""
         hist = self.env.history()
         pay = self.env.payoff()
-        recs = self.policy_records()
+        ply_off, ply_ptr, tiles, visits = self.policy_records_packed()
+        n_plies = len(ply_ptr) - 1
+        if n_plies > 0 and len(visits) > 0:
+            starts = ply_ptr[:-1]
+            totals = np.add.reduceat(visits.astype(np.uint64), np.minimum(starts, len(visits) - 1)).astype(np.float32)
+            counts = np.diff(ply_ptr)
+            totals[counts == 0] = 1.0
+            probs = visits.astype(np.float32) / np.repeat(totals, counts)
+        else:
+            probs = np.zeros(0, dtype=np.float32)
+        pairs = list(zip(tiles.astype(int).tolist(), probs.tolist()))
+        ptr = ply_ptr.tolist()
         out = []
         for g in range(self.n):
-            pols = []
-            for tiles, visits in recs[g]:
-                total = np.float32(visits.sum(dtype=np.uint32))
-                probs = visits.astype(np.float32) / total          # simulation.rs:222, f32 division
-                pols.append(list(zip(tiles.astype(int).tolist(), probs.tolist())))
-            out.append((hist[g][: len(pols)] if len(hist[g]) > len(pols) else hist[g], pols, pay[g].tolist()))
+            a, b = int(ply_off[g]), int(ply_off[g + 1])
+            pols = [pairs[ptr[k]:ptr[k + 1]] for k in range(a, b)]
+            if len(hist[g]) != len(pols):       # simulation.rs:293-295: one policy per history entry, by construction
+                raise ValueError(f"game {g}: {len(hist[g])} plies of history but {len(pols)} searched plies — the game was "
+                                 "advanced outside the search (env.apply / playout), the tuple would be misaligned")
+            out.append((hist[g], pols, pay[g].tolist()))
         return out
 
 

@@ -111,6 +111,26 @@ __global__ void k_legal_rows(const BkState* __restrict__ states, uint32_t* __res
     if (i < n * 20) out[i] = states[i / 20].legal[i % 20];
 }
 
+// Game::get_legal_tiles (game.rs:242-244) in list form: counts[g], then the tiles ascending in tiles[g][0 .. counts[g]).
+// One warp per game: lane r owns row r, a shuffle scan of the row popcounts gives every row its first slot.
+__global__ void k_legal_list(const BkState* __restrict__ states, int32_t* __restrict__ counts, int16_t* __restrict__ tiles, int n) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    uint32_t row = lane < 20 ? states[g].legal[lane] : 0u;
+    const int cnt = __popc(row);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(BK_FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    int pos = incl - cnt;
+    int16_t* out = tiles + size_t(g) * 400;
+    for (; row; row &= row - 1u) out[pos++] = int16_t(lane * 20 + __ffs(row) - 1);
+    if (lane == 31) counts[g] = incl;
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 static int grid_for(int n, int warps) { return (n + warps - 1) / warps; }
 
@@ -354,6 +374,20 @@ int bk_env_legal_rows(bk_env* e, uint32_t* out) {
     BK_LAUNCH(k_legal_rows, (e->n * 20 + 255) / 256, 256, e->stream, e->d_states, d, e->n);
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaMemcpyAsync(out, d, sizeof(uint32_t) * 20 * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaStreamSynchronize(e->stream));
+    return BK_OK;
+}
+
+int bk_env_legal_tiles(bk_env* e, int32_t* counts_out, int16_t* tiles_out) {
+    int rc = env_use(e);
+    if (rc) return rc;
+    if (!counts_out || !tiles_out) return bk_fail(BK_ERR_INVALID_ARG, "null output buffer");
+    int32_t* d_cnt = e->d_i32;
+    int16_t* d_tiles = reinterpret_cast<int16_t*>(e->d_bytes);          // [n][400] int16 fits the [n][2000] byte staging
+    BK_LAUNCH(k_legal_list, grid_for(e->n, 4), 128, e->stream, e->d_states, d_cnt, d_tiles, e->n);
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaMemcpyAsync(counts_out, d_cnt, sizeof(int32_t) * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+    BK_CUDA(cudaMemcpyAsync(tiles_out, d_tiles, sizeof(int16_t) * 400 * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
     BK_CUDA(cudaStreamSynchronize(e->stream));
     return BK_OK;
 }

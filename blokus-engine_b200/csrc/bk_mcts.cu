@@ -828,6 +828,18 @@ int bk_selfplay_training_sizes(bk_selfplay* sp, int64_t* total_plies_out, int64_
     std::vector<BkSearchHdr> h(n);
     BK_CUDA(cudaMemcpyAsync(h.data(), sp->d_hdr, sizeof(BkSearchHdr) * n, cudaMemcpyDeviceToHost, sp->env->stream));
     BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    // The tensors pair history entry k with policy record k and replay the boards from an empty one, which is right only
+    // if every ply of a game was searched by this handle (no bk_env_apply / playout before or between the searches).
+    std::vector<BkSummary> sm(n);
+    BK_LAUNCH(k_sp_summary, (sp->n + 3) / 4, 128, sp->env->stream, sp->env->d_states, sp->env->d_summary, sp->n);
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaMemcpyAsync(sm.data(), sp->env->d_summary, sizeof(BkSummary) * n, cudaMemcpyDeviceToHost, sp->env->stream));
+    BK_CUDA(cudaStreamSynchronize(sp->env->stream));
+    for (size_t g = 0; g < n; ++g)
+        if (uint32_t(sm[g].ply) != h[g].plies_searched)
+            return bk_fail(BK_ERR_STATE, "bk_selfplay_training_sizes: game " + std::to_string(g) + " has " + std::to_string(sm[g].ply) +
+                                             " plies of history but " + std::to_string(h[g].plies_searched) +
+                                             " searched plies: the games were advanced outside the search, the records do not align");
     std::vector<int64_t> off(n + 1, 0);
     for (size_t g = 0; g < n; ++g) off[g + 1] = off[g] + int64_t(h[g].plies_searched);
     if (!sp->d_ply_off) BK_CUDA(cudaMalloc(&sp->d_ply_off, sizeof(int64_t) * (n + 1)));

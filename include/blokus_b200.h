@@ -90,6 +90,9 @@ int bk_env_place_piece(bk_env* env, const int32_t* p, const int32_t* v, const in
 int bk_env_legal_mask(bk_env* env, uint8_t* out);
 /* Same set as 20 row words per game (bit c of out[g][r] = tile r*20+c). */
 int bk_env_legal_rows(bk_env* env, uint32_t* out);
+/* The reference's own shape, `Vec<usize>` (game.rs:242-244): counts_out[g] tiles in tiles_out[g][0 .. counts_out[g]),
+ * ASCENDING (the reference returns HashMap keys in arbitrary order); entries past the count are unspecified. */
+int bk_env_legal_tiles(bk_env* env, int32_t* counts_out, int16_t* tiles_out);
 /* Game::get_board() (game.rs:196-198): the reference's byte encoding, out[g][400]: occupied cell =
  * 0xF0 | owner(1..4); empty cell = OR of 1<<(4+p) over players p with an orthogonal neighbour
  * (board.rs:95-119). */

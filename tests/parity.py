@@ -46,10 +46,12 @@ def compare_state(batch, games, what="all"):
     """Every accessor of the batch against the oracle games (bit-exact)."""
     n = batch.n
     lm = batch.legal_mask()
+    lt = batch.legal_tiles()                     # the list form (bk_env_legal_tiles), ascending
     cur = batch.current_player()
     term = batch.is_terminal()
     for g in range(n):
         assert np.array_equal(lm[g], oracle_mask(games[g].legal_tiles())), f"legal tiles differ, game {g}"
+        assert lt[g] == sorted(games[g].legal_tiles()), f"legal tile list differs, game {g}"
         assert term[g] == games[g].is_terminal()
         assert cur[g] == games[g].current_player(), f"current player differs, game {g}"
     if what != "all":

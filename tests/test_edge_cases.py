@@ -123,3 +123,32 @@ def test_gpu_largest_batch_config5_shard(cuda_lib, orc):
     and a sample is checked ply by ply against the oracle."""
     res = parity.check_playout(cuda_lib, orc, n_games=8192, seed=31, first_game_id=3 * 8192, n_check=64)
     assert res["steps"].min() >= 200
+
+
+def _misaligned_records_suite(lib, buffers):
+    """Games advanced OUTSIDE the search (env.apply before it) have more history than policy records: the training
+    tensors and the reference tuple would be misaligned, so both refuse (round-1 advisor finding)."""
+    cfg = Config(sims_per_move=8, sample_moves=2, c_base=19652, c_init=1.25, dirichlet_alpha=0.3, exploration_fraction=0.25, seed=2)
+    sp = SelfPlay(2, cfg, lib=lib)
+    sp.env.apply([0, 0])                           # one ply played by hand
+    sp.run_stub(3)
+    with pytest.raises(BkError) as e:
+        sp.training_tensors(buffers=buffers)
+    assert e.value.code == -5 and "do not align" in str(e.value)
+    with pytest.raises(ValueError):
+        sp.game_data()
+    sp.close()
+    ok = SelfPlay(2, cfg, lib=lib)
+    ok.run_stub(3)
+    st, po, va, offs = ok.training_tensors(buffers=buffers)
+    assert len(st) == 6 and offs.tolist() == [0, 3, 6] and len(ok.game_data()[1][0]) == 3
+    ok.close()
+
+
+def test_emu_misaligned_records_are_refused(emu_lib):
+    _misaligned_records_suite(emu_lib, parity.HostBuffers())
+
+
+@pytest.mark.gpu
+def test_gpu_misaligned_records_are_refused(cuda_lib):
+    _misaligned_records_suite(cuda_lib, None)
