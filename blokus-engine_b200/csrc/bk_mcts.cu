@@ -108,15 +108,25 @@ k_selfplay_stub_pipe(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* his
     __shared__ BkWarpSmem wsm;
     __shared__ BkPathBuf pbs[2];
     __shared__ BkPipeShared ps;
+    __shared__ float s_ucb[BK_PIPE_TAB_CAP], s_rcp[BK_PIPE_TAB_CAP];
     const BkTabs tabs = bk_stage_tables(smem_tabs);
+    // the UCB factor tables (sims + 2 and sims + 3 floats) in shared memory when they fit
+    const bool tabs_fit = cfg.sims + 3u <= BK_PIPE_TAB_CAP;
+    if (tabs_fit)
+        for (uint32_t i = threadIdx.x; i < cfg.sims + 3u; i += blockDim.x) {
+            s_ucb[i] = i < cfg.sims + 2u ? cfg.ucb_tab[i] : 0.0f;
+            s_rcp[i] = cfg.rcp_tab ? cfg.rcp_tab[i] : 0.0f;
+        }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     if (g >= n) return;
     const BkTree tr = bk_tree_of(pl, cfg, g);
+    const float* ucb = tabs_fit ? s_ucb : cfg.ucb_tab;
+    const float* rcp = cfg.rcp_tab ? (tabs_fit ? s_rcp : cfg.rcp_tab) : nullptr;
     kb_selfplay_stub_pipe(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
                           pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies, counters, g,
-                          warp, lane, tabs, wsm, pbs, ps);
+                          warp, lane, tabs, wsm, pbs, ps, ucb, rcp);
 }
 
 __global__ void __launch_bounds__(32 * 4) k_sp_begin(BkSearchCfg cfg, BkPools pl, const BkState* states, int n) {

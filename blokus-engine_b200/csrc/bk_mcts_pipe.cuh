@@ -24,6 +24,7 @@
 #include "bk_mcts_kernels.cuh"
 
 #define BK_TN_TERMINAL(tn) (((tn) >> 22) & 1u)
+#define BK_PIPE_TAB_CAP 1024      // UCB factor tables up to this many entries are staged in shared memory
 
 // -DBK_PIPE_STATS (probe builds only, tools/probe_mcts_pipe.py): cycles each warp spends waiting for the other go to
 // counters[6] (A) / [7] (B), a game's total cycles to [8]; finer sums over all games to g_pipe_stats:
@@ -97,19 +98,32 @@ struct BkPipeLeaf {
 
 // select_child loop (simulation.rs:198-203, :88-98, :135-147); same arithmetic as bk_tree_select<false>.
 // `pending` = the entry warp B is expanding right now (BK_NODE_NONE if none): arriving there ends the walk.
-__device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkSearchCfg& cfg, const BkBlock& root, uint32_t root_visits,
+// ucb / rcp: the two small tables of the UCB factor (cfg.ucb_tab, cfg.rcp_tab) — copies in shared memory when they fit
+// (BK_PIPE_TAB_CAP): both loads sit on the select's dependent chain, and this kernel's L1 is too contended to serve them.
+__device__ __forceinline__ float bk_pipe_u(const float* __restrict__ rcp, float F, uint32_t n_visits) {      // see bk_ucb_div
+    if (rcp) {
+        const float r = rcp[n_visits + 1u];
+        const float d = float(n_visits + 1u);
+        const float q0 = __fmul_rn(F, r);
+        return __fmaf_rn(__fmaf_rn(-d, q0, F), r, q0);
+    }
+    return __fdiv_rn(F, __fadd_rn(1.0f, float(n_visits)));
+}
+
+__device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const float* __restrict__ ucb, const float* __restrict__ rcp,
+                                                     const BkBlock& root, uint32_t root_visits,
                                                      uint32_t pending, int lane, BkPathBuf& pb, uint32_t& err) {
     uint32_t node = 0u, off = root.off, Np = root_visits, e = 0u, tn = 0u, mask = 0u;
     int n = int(root.n), depth = 0, kind = BK_SEL_LEAF;
     for (;;) {
-        const float F = cfg.ucb_tab[Np];
+        const float F = ucb[Np];
         uint32_t wi, b_tn = 0u, b_n = 0u, b_w = 0u, b_off = 0u, b_node = 0u;
         if (n <= 32) {
             uint32_t key = 0u;
             if (lane < n) {
                 const uint4 sv = tr.S[off + lane];
                 const uint4 xv = tr.X[off + lane];
-                const float u = bk_ucb_div(cfg, F, sv.x);
+                const float u = bk_pipe_u(rcp, F, sv.x);
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
                 if (sc >= 0.0f) key = __float_as_uint(sc) + 1u;
                 b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z;
@@ -122,10 +136,13 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
             int bi = -1;
             for (int i = lane; i < n; i += 32) {
                 const uint4 sv = tr.S[off + i];
-                const uint4 xv = tr.X[off + i];
-                const float u = bk_ucb_div(cfg, F, sv.x);
+                const float u = bk_pipe_u(rcp, F, sv.x);
                 const float sc = __fadd_rn(__fmul_rn(u, __uint_as_float(sv.z)), __uint_as_float(sv.y));
-                if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; b_w = xv.x; b_off = xv.y; b_node = xv.z; }
+                if (sc >= best) { best = sc; bi = i; b_tn = sv.w; b_n = sv.x; }
+            }
+            if (bi >= 0) {                       // the descent stream of this lane's best only (in flight while the warp reduces)
+                const uint4 xv = tr.X[off + bi];
+                b_w = xv.x; b_off = xv.y; b_node = xv.z;
             }
             const uint32_t key = bi >= 0 ? __float_as_uint(best) + 1u : 0u;
             const uint32_t kmax = __reduce_max_sync(BK_FULL, key);
@@ -135,7 +152,10 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
         const int src = int(wi & 31u);
         e = off + wi;
         if (e == pending) { kind = BK_SEL_HIT_PENDING; break; }      // B has not finished this leaf: its flags are not to be trusted
-        tn = __shfl_sync(BK_FULL, b_tn, src);
+        tn = __shfl_sync(BK_FULL, b_tn, src);                       // the four broadcasts are issued back to back: the next
+        const uint32_t w_n = __shfl_sync(BK_FULL, b_n, src);         // level's loads wait for one shuffle latency, not two
+        const uint32_t w_off = __shfl_sync(BK_FULL, b_off, src);
+        const uint32_t w_node = __shfl_sync(BK_FULL, b_node, src);
         if (lane == src) {
             const int slot = depth & (BK_PATH_CAP - 1);
             pb.e[slot] = e; pb.n[slot] = b_n; pb.w[slot] = b_w;
@@ -143,12 +163,10 @@ __device__ __forceinline__ BkPipeLeaf bk_pipe_select(const BkTree& tr, const BkS
         }
         ++depth;
         if (!BK_TN_EXPANDED(tn)) {
-            if (BK_TN_TERMINAL(tn)) { kind = BK_SEL_KNOWN_TERMINAL; mask = __shfl_sync(BK_FULL, b_off, src); }
+            if (BK_TN_TERMINAL(tn)) { kind = BK_SEL_KNOWN_TERMINAL; mask = w_off; }
             break;
         }
-        Np = __shfl_sync(BK_FULL, b_n, src);
-        off = __shfl_sync(BK_FULL, b_off, src);
-        node = __shfl_sync(BK_FULL, b_node, src);
+        Np = w_n; off = w_off; node = w_node;
         n = int(BK_TN_NCHILD(tn));
     }
     if (depth > BK_PATH_CAP) { err |= BK_SP_ERR_PATH_CAP; kind = BK_SEL_ERROR; }
@@ -245,7 +263,8 @@ __device__ __forceinline__ uint32_t bk_pipe_wait(BkPipeShared& ps, uint32_t seq,
 
 // runs cfg.sims simulations of one ply; returns the error flags raised on this side
 __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const BkTree& tr, const BkBlock& root, BkPipeShared& ps,
-                                                   int lane, BkPathBuf (&pbs)[2], BkSpCounters& ctr, unsigned long long& waited) {
+                                                   int lane, BkPathBuf (&pbs)[2], BkSpCounters& ctr, unsigned long long& waited,
+                                                   const float* __restrict__ ucb, const float* __restrict__ rcp) {
     uint32_t err = 0u, started = 0u, seq = 0u, pending = BK_NODE_NONE;
     int cur = 0, pend_depth = 0;
     bool inflight = false;
@@ -266,7 +285,7 @@ __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const
             break;
         }
         BK_STAT_T0(ts0);
-        const BkPipeLeaf lf = bk_pipe_select(tr, cfg, root, started + 1u, pending, lane, pbs[cur], err);   // root visits: :194
+        const BkPipeLeaf lf = bk_pipe_select(tr, ucb, rcp, root, started + 1u, pending, lane, pbs[cur], err);   // root visits: :194
         BK_STAT_T1(ts0, 0);
         BK_STAT_ADD(1, lf.depth);
         BK_STAT_ADD(5, 1);
@@ -317,7 +336,8 @@ __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, Bk
                                                       const BkTree& tr, BkSearchHdr* hdr_g, uint32_t* pol_off, uint16_t* pol_tile,
                                                       uint32_t* pol_visits, int max_plies, unsigned long long* counters, int g,
                                                       int warp, int lane, const BkTabs& tabs, BkWarpSmem& sm,
-                                                      BkPathBuf (&pbs)[2], BkPipeShared& ps) {
+                                                      BkPathBuf (&pbs)[2], BkPipeShared& ps, const float* __restrict__ ucb,
+                                                      const float* __restrict__ rcp) {
     BkRegs G;
     BkSearchHdr hd;
     BkCounters gctr = {0u, 0u};
@@ -354,7 +374,7 @@ __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, Bk
         __syncthreads();
         if (!ps.go) break;
         if (warp == 0) {
-            hd.err |= bk_pipe_search(cfg, tr, root, ps, lane, pbs, ctr, waited);
+            hd.err |= bk_pipe_search(cfg, tr, root, ps, lane, pbs, ctr, waited, ucb, rcp);
         } else {
             bk_pipe_leaf_worker(cfg, tr, ps, lane, tabs, sm, gctr, ctr, waited);
         }

@@ -33,7 +33,7 @@ for flags, k in MODES:
     sp.set_mode(flags, k)
     if k == 1:
         sp.run_stub(5 if quick else 7)
-    sp.run_evaluator(batched, max_plies=4 if quick else 6, xp="numpy")
-    sp.policy_records(); sp.policy_records_packed(); sp.last_root(); sp.training_tensors(xp="numpy")
+    sp.run_evaluator(batched, max_plies=4 if quick else 6, buffers=parity.HostBuffers())
+    sp.policy_records(); sp.policy_records_packed(); sp.last_root(); sp.training_tensors(buffers=parity.HostBuffers())
     sp.close()
 print("sanitize target done")
