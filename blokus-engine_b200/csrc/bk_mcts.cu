@@ -93,7 +93,7 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
     const int g = blockIdx.x;
     if (g >= n) return;
     const BkTree tr = bk_tree_of(pl, cfg, g);
-    kb_selfplay_stub(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+    kb_selfplay_stub<(MINB < 16)>(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
                      pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies,
                      counters, g, lane, tabs, wsm);
 }

@@ -316,7 +316,10 @@ __device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn,
 // VL (multi-leaf throughput mode): every entry on the way down gets its visit at once — a visit worth 0
 // until the value arrives, i.e. a virtual loss (Q = W / (N + 1)) that steers the next selections of the
 // same round elsewhere; the backup then only adds the value.  One warp owns the tree, so no atomics.
-template <bool VL>
+// PF: ask L2 for the node state the leaf step will load, one level ahead.  It pays when a few games per SM are bound by
+// latency (1024 games: the one-warp kernel), and costs 3 % when many resident games are bound by L2 / DRAM traffic (8192 games:
+// the prefetches are half of the DRAM reads), so the high-residency instantiations switch it off.
+template <bool VL, bool PF = true>
 __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                                  const BkBlock& root, int lane, BkWarpSmem& sm) {
     uint32_t node = 0u;
@@ -329,7 +332,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
     for (;;) {
         // If this level's winner turns out to be a leaf, the state of `node` is what the leaf step loads
         // next: ask L2 for its 5 lines now, one level of latency ahead.
-        bk_prefetch_state(&tr.nodes[node], lane);
+        if (PF) bk_prefetch_state(&tr.nodes[node], lane);
         const float F = cfg.ucb_tab[Np];
         uint32_t wi, b_tn = 0u, b_n = 0u, b_w = 0u, b_off = 0u, b_node = 0u;
         if (n <= 32) {
@@ -578,11 +581,12 @@ __device__ __forceinline__ BkBlock bk_tree_resume(const BkTree& tr, BkSearchHdr&
 
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
 // evaluate (terminal payoff, or stub value + expansion), back up.
+template <bool PF>
 __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
                                             const BkBlock& root, int lane, const BkTabs& tabs, BkWarpSmem& sm,
                                             BkCounters& gctr, BkSpCounters& ctr) {
     hd.root_visits += 1u;                                                        // simulation.rs:194
-    const BkLeaf lf = bk_tree_select<false>(tr, hd, cfg, root, lane, sm);
+    const BkLeaf lf = bk_tree_select<false, PF>(tr, hd, cfg, root, lane, sm);
     if (!lf.ok) return;
     BkRegs L;
     bk_load(&tr.nodes[lf.parent], lane, L);
@@ -607,6 +611,7 @@ __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, c
 }
 
 // training_game() (simulation.rs:267-296) with the stub evaluator, up to max_plies plies, on one warp.
+template <bool PF>
 __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState* __restrict__ states,
                                                  uint16_t* __restrict__ hist, const BkTree& tr, BkSearchHdr* hdr_g,
                                                  uint32_t* pol_off, uint16_t* pol_tile, uint32_t* pol_visits,
@@ -637,7 +642,7 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         }
         if (search) {
             bk_tree_noise(tr, cfg, game_id, G.ply, lane);                              // :190
-            while (hd.sims_done < cfg.sims && hd.err == 0u) bk_sim_stub(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
+            while (hd.sims_done < cfg.sims && hd.err == 0u) bk_sim_stub<PF>(tr, hd, cfg, root, lane, tabs, sm, gctr, ctr);
         }
         if (hd.err) break;
         uint32_t played = 0u;
