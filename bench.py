@@ -258,7 +258,7 @@ def mcts_cpu_baseline(games: int = 0) -> dict:
     self_play/src/simulation.rs, one game per thread (the reference's own parallelism: one process per game)."""
     from oracle import oracle as orc
     thr = host_threads()
-    games = games or max(16, thr)
+    games = games or thr            # one complete game per host thread (16 on the single-GPU boxes, 32 on the 8-GPU ones): one wave
     cfg = orc.make_config(**{**MCTS_CFG, "c_base": 19652.0})
     r = orc.selfplay_batch(cfg, 0, games, n_threads=thr, max_plies=-1)
     return {"value": r["sims"] / r["seconds"], "unit": "sims/s", "cores": thr, "kind": "port",
@@ -318,7 +318,7 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true", help="skip the secondary MCTS sims/s measurement")
     ap.add_argument("--mcts-plies", type=int, default=-1, help="plies per game in the MCTS measurement (<0: whole games)")
-    ap.add_argument("--mcts-cpu-games", type=int, default=0, help="complete games of the CPU MCTS sample (0: max(16, host threads))")
+    ap.add_argument("--mcts-cpu-games", type=int, default=0, help="complete games of the CPU MCTS sample (0: one per host thread)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the extra.env_sustained loop")
     ap.add_argument("--no-config5", action="store_true", help="skip extra.config5_shard (8192 complete games per GPU)")
     args = ap.parse_args()

@@ -346,3 +346,31 @@ def test_gpu_training_rounds_script(cuda_lib):
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 2 and lines[1]["buffer"] == 72 and lines[1]["steps"] == 6
     assert all(l["new_samples"] == 36 and l["policy_loss"] == l["policy_loss"] for l in lines)   # 6 games x 6 plies, finite losses
+
+
+@pytest.mark.gpu
+def test_gpu_run_network_equals_run_evaluator(cuda_lib):
+    """bk_selfplay_run_network (planes written straight into the first convolution's input, the whole round inside the
+    library) against SelfPlay.run_evaluator driving the SAME native evaluator through float planes: identical histories and
+    policy records — in the exact mode and with multi-leaf rounds + forced-ply shortcut + tree reuse (dense rows)."""
+    from blokus_self_play import SelfPlay, Config, MODE_SKIP_FORCED, MODE_TREE_REUSE
+    from blokus_self_play.resnet import ResNet
+    from blokus_self_play.tc_resnet import TensorCoreLeafEvaluator
+    torch.manual_seed(23)
+    model = ResNet(2, 256).cuda().eval()
+    ev = TensorCoreLeafEvaluator(model, lib=cuda_lib, max_rows=256)
+    cfg = Config(sims_per_move=40, sample_moves=4, c_base=19652, c_init=1.25, dirichlet_alpha=0.3, exploration_fraction=0.25, seed=31)
+    for flags, leaves, plies in ((0, 1, 6), (MODE_SKIP_FORCED | MODE_TREE_REUSE, 4, 9)):
+        a = SelfPlay(40, cfg, first_game_id=5, lib=cuda_lib)
+        a.set_mode(flags, leaves)
+        ia = a.run_network(ev, max_plies=plies)
+        b = SelfPlay(40, cfg, first_game_id=5, lib=cuda_lib)
+        b.set_mode(flags, leaves)
+        ib = b.run_evaluator(ev, max_plies=plies)
+        assert ia["rounds"] == ib["rounds"] and ia["evals"] > 0
+        assert a.env.history() == b.env.history()
+        for ra, rb in zip(a.policy_records(), b.policy_records()):
+            assert len(ra) == len(rb) == plies
+            for (t1, v1), (t2, v2) in zip(ra, rb):
+                assert np.array_equal(t1, t2) and np.array_equal(v1, v2) and int(v1.sum()) == 40
+        a.close(); b.close()
