@@ -225,7 +225,11 @@ static int env_fetch(bk_env* e, int32_t* plies_out, int32_t* scores_out, uint16_
 extern "C" {
 
 const char* bk_last_error(void) { return g_last_error.c_str(); }
-const char* bk_version(void) { return "blokus-engine_b200 0.1 (sm_100a)"; }
+#ifdef BK_WARP_EMU
+const char* bk_version(void) { return "blokus-engine_b200 0.2 (CPU warp emulator of the kernel sources: tests only)"; }
+#else
+const char* bk_version(void) { return "blokus-engine_b200 0.2 (sm_100a)"; }
+#endif
 int bk_device_count(void) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }

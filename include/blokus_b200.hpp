@@ -42,6 +42,14 @@ public:
         check(bk_env_place_piece(env_, p.data(), v.data(), o.data(), nullptr));               // game.rs:116
     }
     std::vector<uint8_t> legal_mask() const { return bytes(bk_env_legal_mask, 400); }        // game.rs:242
+    // Game::get_legal_tiles of game g in the reference's own shape (Vec<usize>; ascending here), bk_env_legal_tiles
+    std::vector<int> legal_tiles(int g) const {
+        const size_t n = static_cast<size_t>(n_);
+        std::vector<int32_t> cnt(n);
+        std::vector<int16_t> tiles(n * 400);
+        check(bk_env_legal_tiles(env_, cnt.data(), tiles.data()));
+        return std::vector<int>(tiles.begin() + long(g) * 400, tiles.begin() + long(g) * 400 + cnt[size_t(g)]);
+    }
     std::vector<uint8_t> board() const { return bytes(bk_env_board, 400); }                  // game.rs:196
     std::vector<uint8_t> board_state() const { return bytes(bk_env_board_state, 2000); }     // game.rs:283
     std::vector<uint8_t> anchors(int player = -1) const {                                    // game.rs:238
@@ -100,12 +108,7 @@ public:
     Game place_piece(int p, int v, int o) const { Game ns = *this; ns.b_.place_piece({p}, {v}, {o}); return ns; }
     std::vector<uint8_t> get_board() const { return b_.board(); }
     int current_player() const { return b_.current_player()[0]; }
-    std::vector<int> get_legal_tiles() const {
-        std::vector<int> out;
-        const auto m = b_.legal_mask();
-        for (int t = 0; t < 400; ++t) if (m[size_t(t)]) out.push_back(t);
-        return out;
-    }
+    std::vector<int> get_legal_tiles() const { return b_.legal_tiles(0); }                  // game.rs:242 (ascending)
     std::vector<int> get_current_anchors() const {
         std::vector<int> out;
         const auto m = b_.anchors(-1);
@@ -167,6 +170,29 @@ struct TrainingGame {
     std::vector<float> values;                                // payoff, absolute seat order
 };
 
+// The policy/value network `ResNet(blocks, 256)` (model/resnet.py:44-94, eval mode) resident on one device as a
+// bk_evaluator: what the reference's inference server computes per batch (model/training.py:43-67), on this library's
+// kernels.  Parameters are host arrays with the BatchNorms already folded (layout: blokus_b200.h, bk_evaluator_create).
+class Evaluator {
+public:
+    Evaluator(int device, int blocks, int max_rows, const uint16_t* w_in, const float* b_in, const uint16_t* w_blocks,
+              const float* b_blocks, const float* head_w, const float* head_affine, const float* lin_w, const float* lin_b) {
+        check(bk_evaluator_create(device, blocks, max_rows, w_in, b_in, w_blocks, b_blocks, head_w, head_affine, lin_w, lin_b, &ev_));
+    }
+    Evaluator(const Evaluator&) = delete;
+    Evaluator& operator=(const Evaluator&) = delete;
+    ~Evaluator() { bk_evaluator_destroy(ev_); }
+    bk_evaluator* handle() const { return ev_; }
+    int max_rows() const { return bk_evaluator_max_rows(ev_); }
+    // model(boards): device planes [rows][5][20][20] f32 -> device policy [rows][400], value [rows][4]
+    void forward(const float* dev_planes, int rows, float* dev_policy, float* dev_value, void* cuda_stream = nullptr) {
+        check(bk_evaluator_forward(ev_, dev_planes, rows, dev_policy, dev_value, nullptr, nullptr, cuda_stream));
+    }
+
+private:
+    bk_evaluator* ev_ = nullptr;
+};
+
 // n self-play clients on one device; game g has global id first_game_id + g.
 class SelfPlay {
 public:
@@ -209,6 +235,13 @@ public:
             }
             check(bk_selfplay_end_ply(sp_));
         }
+    }
+    // training_game() with the native network evaluator: the whole round stays inside the library (bk_selfplay_run_network)
+    struct NetworkRun { int64_t rounds = 0, evals = 0; };
+    NetworkRun run_network(Evaluator& ev, int max_plies = -1) {
+        NetworkRun r;
+        check(bk_selfplay_run_network(sp_, ev.handle(), max_plies, &r.rounds, &r.evals));
+        return r;
     }
     std::vector<TrainingGame> results() const {
         const size_t n = static_cast<size_t>(n_);
