@@ -373,6 +373,9 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
         if (const char* e = getenv("BK_STUB_MIN_BLOCKS")) sp->stub_min_blocks = atoi(e);
     }
 #endif
+#ifdef BK_WARP_EMU
+    sp->stub_pipe = 0;       // the CPU emulator pays a futex per mailbox poll: the pipeline runs there only when a test asks for it
+#endif
     if (const char* e = getenv("BK_STUB_PIPE")) sp->stub_pipe = atoi(e);     // probes / tests: 0 = one-warp kernel, 1 = pipeline
     int rc = bk_env_create(n_games, device, &sp->env);
     if (rc) { delete sp; return rc; }

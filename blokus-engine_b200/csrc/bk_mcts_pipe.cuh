@@ -62,6 +62,15 @@ struct BkPipeShared {
 #define BK_PIPE_TERMINAL 1u
 #define BK_PIPE_ERROR 2u
 
+// The tests' CPU emulator runs every lane as an OS thread: a polling warp must give its cores away there.
+#ifdef BK_WARP_EMU
+#include <chrono>
+#include <thread>
+#define BK_PIPE_POLL_PAUSE() std::this_thread::yield()
+#else
+#define BK_PIPE_POLL_PAUSE() do {} while (0)
+#endif
+
 __device__ __forceinline__ uint32_t bk_pipe_read(const volatile uint32_t* p, int lane) {   // warp-uniform read of a flag
     uint32_t v = 0u;
     if (lane == 0) v = *p;
@@ -206,6 +215,7 @@ __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, cons
                 have = bk_pipe_read(&ps.req_seq, lane);
                 if (have != seq) break;
                 if (bk_pipe_read(&ps.quit, lane)) break;
+                BK_PIPE_POLL_PAUSE();
             }
             BK_PIPE_T1(waited);
         }
@@ -255,7 +265,7 @@ __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, cons
 // ---- warp A: select + backup, one simulation ahead of B -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bk_pipe_wait(BkPipeShared& ps, uint32_t seq, int lane, unsigned long long& waited) {
     BK_PIPE_T0();
-    while (bk_pipe_read(&ps.done_seq, lane) != seq) {}
+    while (bk_pipe_read(&ps.done_seq, lane) != seq) { BK_PIPE_POLL_PAUSE(); }
     BK_PIPE_T1(waited);
     __threadfence_block();
     return bk_pipe_read(&ps.res_kind, lane);

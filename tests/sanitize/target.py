@@ -36,4 +36,11 @@ for flags, k in MODES:
     sp.run_evaluator(batched, max_plies=4 if quick else 6, buffers=parity.HostBuffers())
     sp.policy_records(); sp.policy_records_packed(); sp.last_root(); sp.training_tensors(buffers=parity.HostBuffers())
     sp.close()
+# the two-warp pipelined stub kernel (the emulator build only runs it on request)
+os.environ["BK_STUB_PIPE"] = "1"
+sp = SelfPlay(1, cfg, first_game_id=11, lib=lib)
+del os.environ["BK_STUB_PIPE"]
+sp.run_stub(3 if quick else 5)
+sp.policy_records(); sp.last_root()
+sp.close()
 print("sanitize target done")

@@ -153,5 +153,5 @@ def _pipeline_equals_one_warp_kernel(lib, n_games, sims, max_plies):
 
 
 def test_emu_pipeline_equals_one_warp_kernel(emu_lib):
-    h = _pipeline_equals_one_warp_kernel(emu_lib, 2, 10, -1)
+    h = _pipeline_equals_one_warp_kernel(emu_lib, 1, 8, -1)
     assert all(len(x) > 200 for x in h)
