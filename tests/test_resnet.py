@@ -38,6 +38,19 @@ def test_forward_matches_reference_cpu_fp32():
     assert np.allclose(value.numpy().sum(axis=1), 1.0, atol=1e-6)
 
 
+def test_reference_checkpoint_loads_and_evaluates():
+    """The reference's own trained checkpoint (weights/model_1.pt, ResNet(2,16)) loads with strict=True into this
+    repo's model and gives the outputs the reference's model/resnet.py gave (tests/golden/make_resnet_ckpt_golden.py)."""
+    from blokus_self_play.resnet import ResNet
+    z = np.load(os.path.join(os.path.dirname(GOLD), "resnet_ckpt_model1.npz"))
+    model = ResNet(2, 16, False)                  # the reference's constructor call (training.py:169) has three arguments
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=True)
+    with torch.no_grad():
+        policy, value = model.eval()(torch.from_numpy(z["planes"]))
+    assert np.allclose(policy.numpy(), z["policy"], atol=1e-6, rtol=0) and np.allclose(value.numpy(), z["value"], atol=1e-6, rtol=0)
+    assert float(z["policy"].max()) > 0.05        # a trained, non-uniform policy
+
+
 @pytest.mark.gpu
 def test_forward_matches_reference_on_gpu():
     from blokus_self_play.resnet import LeafEvaluator
