@@ -233,3 +233,12 @@ def test_gpu_pipeline_equals_one_warp_kernel(cuda_lib):
     from test_emu_mcts import _pipeline_equals_one_warp_kernel
     h = _pipeline_equals_one_warp_kernel(cuda_lib, 24, 200, -1)
     assert all(len(x) > 200 for x in h)
+
+
+def test_gpu_pipeline_tables_beyond_shared_memory(cuda_lib):
+    """1100 simulations per move: the UCB factor tables no longer fit the pipelined kernel's shared-memory staging
+    (1024 entries) and are read from global memory; 5000: the exhaustive check of the short division is skipped
+    (sims > 4096) and the kernels use the IEEE division.  Both still equal the one-warp kernel bit for bit."""
+    from test_emu_mcts import _pipeline_equals_one_warp_kernel
+    _pipeline_equals_one_warp_kernel(cuda_lib, 8, 1100, 3)
+    _pipeline_equals_one_warp_kernel(cuda_lib, 4, 5000, 1)
