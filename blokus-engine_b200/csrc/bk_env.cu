@@ -48,6 +48,7 @@ k_place_piece(BkState* __restrict__ states, uint16_t* __restrict__ hist, const i
 // One warp per CTA: the hardware CTA scheduler balances games of different length over the SMs.
 // 32 CTAs (games) per SM is the hardware's CTA limit: 64 registers.  (A 28-per-SM build — 68 registers, enough for
 // config 2's 27.7 games per SM — measured the same on one batch and 2 % slower with two batches in flight.)
+template <bool HASH>
 __global__ void __launch_bounds__(32, 32)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
           const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
@@ -56,9 +57,10 @@ k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint
     const BkTabs tabs = bk_stage_tables(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int g = blockIdx.x;                     // launched with one warp per CTA: the game index is CTA-uniform
     if (g >= n) return;
-    kb_playout(states, hist, seed, ids ? ids[g] : first_id + uint32_t(g), max_plies, flags, steps_out, hash_out, counters, g, lane, tabs);
+    const uint32_t game_id = __reduce_or_sync(BK_FULL, ids ? ids[g] : first_id + uint32_t(g));   // uniform for the compiler too
+    kb_playout<HASH>(states, hist, seed, game_id, max_plies, flags, steps_out, hash_out, counters, g, lane, tabs);
 }
 
 __global__ void k_scores(const BkState* __restrict__ states, int32_t* __restrict__ plies, int32_t* __restrict__ scores, int n) {
@@ -466,8 +468,13 @@ static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const u
     }
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    BK_LAUNCH(k_playout, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
-              flags, e->d_i32, e->d_hash, e->d_counters);
+    // the per-ply state digest is its own instantiation: the plain playout carries neither its registers nor its code
+    if (flags & BK_PLAYOUT_HASH_FLAG)
+        BK_LAUNCH(k_playout<true>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+                  flags, e->d_i32, e->d_hash, e->d_counters);
+    else
+        BK_LAUNCH(k_playout<false>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
+                  flags, e->d_i32, e->d_hash, e->d_counters);
     return env_finish_timed(e, false);
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include "bk_game.cuh"
 #include "bk_rng.cuh"
+#include "bk_playout.cuh"
 
 #ifndef BK_ERR_ILLEGAL_MOVE_CODE
 #define BK_ERR_ILLEGAL_MOVE_CODE (-3)
@@ -119,7 +120,68 @@ __device__ __forceinline__ void kb_place_piece(BkState* __restrict__ states, uin
     if (lane == 0) status[g] = ok ? 0 : BK_ERR_ILLEGAL_MOVE_CODE;
 }
 
-// Persistent lockstep playout: one warp plays its game to the end without leaving the SM.
+// Persistent lockstep playout: one warp plays its game to the end without leaving the SM.  bk_playout.cuh keeps the
+// turn in progress in registers and touches the bitboards once per piece.
+struct BkPlayoutCtx {
+    uint64_t seed;
+    uint32_t game_id, flags, ply_end;
+    uint16_t* __restrict__ h16;
+    uint64_t h;
+};
+
+template <bool HASH>
+__device__ __forceinline__ void bk_playout_digest(BkPlayoutCtx& C, const BkRegs& G, const BkTurn& T, int p, int tile, int lane) {
+    if (!HASH) return;
+    BkRegs H = G;
+    if (T.nT) bk_turn_materialise(H, T, lane);
+    C.h = bk_splitmix64(C.h ^ bk_digest(H, lane));
+    C.h = bk_splitmix64(C.h ^ (uint64_t(p) | (uint64_t(tile) << 8)));
+}
+
+__device__ __forceinline__ int bk_playout_draw(const BkPlayoutCtx& C, uint32_t ply, int cnt, BkPlayoutRng& rng) {
+    if (C.flags & BK_PLAYOUT_MIN_TILE_FLAG) return 0;
+    if (C.flags & BK_PLAYOUT_MAX_TILE_FLAG) return cnt - 1;
+    return int(bk_playout_index(C.seed, C.game_id, ply, uint32_t(cnt), rng));
+}
+
+// the moves of a turn after its first tile, until the piece is complete (legal set empty) or the ply budget ends
+template <bool HASH>
+__device__ __forceinline__ void bk_playout_turn_moves(BkPlayoutCtx& C, BkRegs& G, BkTurn& T, BkPlayoutRng& rng, int p,
+                                                      int lane, const BkTabs& tabs) {
+    while ((T.w0 | T.w1 | T.w2) != 0u && G.ply < C.ply_end) {
+        const int c0 = __popc(T.w0), c1 = __popc(T.w1), cnt = c0 + c1 + __popc(T.w2);
+        const int idx = bk_playout_draw(C, G.ply, cnt, rng);
+        int k, wbit;
+        uint32_t b;
+        bk_turn_pick(T, idx, c0, c1, k, b, wbit);
+        const int tile = bk_window_tile(wbit, T.tr, T.tc);
+        T.tq = (T.tq << 7) | uint32_t(wbit);
+        T.nT += 1;
+        bk_turn_next(G, T, k, b, lane, tabs);
+        if (lane == 0 && G.ply < BK_HIST_CAP) C.h16[G.ply] = uint16_t(tile | (p << 9));
+        G.ply += 1u;
+        if (HASH && (T.w0 | T.w1 | T.w2) != 0u) bk_playout_digest<HASH>(C, G, T, p, tile, lane);
+        if (HASH) T.last = tile;
+    }
+}
+
+// game.rs:176-191: the piece is complete — its squares join the mover's board, the piece leaves the hand, its size
+// is remembered, the turn passes
+template <bool HASH>
+__device__ __forceinline__ void bk_playout_commit(BkPlayoutCtx& C, BkRegs& G, BkTurn& T, int p, int lane,
+                                                  const BkTabs& tabs, BkCounters& ctr) {
+    const int pid = bk_turn_piece(G, T, lane, tabs);
+    const uint32_t rows = bk_window_to_row(G.tw0, G.tw1, G.tw2, T.tr, T.tc, lane);
+    const uint32_t clr = ~(1u << pid);
+    if (p == 0) { G.o0 |= rows; G.pc0 &= clr; } else if (p == 1) { G.o1 |= rows; G.pc1 &= clr; }
+    else if (p == 2) { G.o2 |= rows; G.pc2 &= clr; } else { G.o3 |= rows; G.pc3 &= clr; }
+    G.lastlens = (G.lastlens & ~(0xFFu << (8 * p))) | (uint32_t(T.nT) << (8 * p));
+    T.nT = 0;
+    bk_advance(G, lane, ctr);
+    if (HASH) bk_playout_digest<HASH>(C, G, T, p, T.last, lane);
+}
+
+template <bool HASH>
 __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, uint64_t seed,
                                            uint32_t game_id, int max_plies, uint32_t flags,
                                            int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
@@ -127,39 +189,44 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     BkRegs G;
     bk_load(&states[g], lane, G);
     BkCounters ctr = {0u, 0u};
-    uint16_t* __restrict__ h16 = hist + size_t(g) * BK_HIST_CAP;
-    uint64_t h = 0ull;
-    int steps = 0;
+    BkPlayoutCtx C;
+    C.seed = seed; C.game_id = game_id; C.flags = flags; C.h = 0ull;
+    C.h16 = hist + size_t(g) * BK_HIST_CAP;
+    C.ply_end = max_plies < 0 ? 0xffffffffu : G.ply + uint32_t(max_plies);
     BkPlayoutRng rng;
     rng.w0 = rng.w1 = rng.w2 = rng.w3 = 0u;
     rng.block = 0xffffffffu;
-    // While a turn is in progress the legal set lives in its 9x9-window form (warp-uniform words): counting and
-    // picking the idx-th tile are scalar there, and the board rows (G.legal) are only materialised on demand.
-    BkNarrow nw;
-    nw.w0 = nw.w1 = nw.w2 = 0u; nw.tr = nw.tc = 0; nw.pid = -1; nw.any_valid = false;
-    bool mid = false;                     // the loop starts from a stored state: its rows are valid
-    while (!bk_terminal(G) && (max_plies < 0 || steps < max_plies)) {
-        const int cnt = mid ? bk_narrow_count(nw) : bk_legal_count(G.legal);
-        int idx;
-        if (flags & BK_PLAYOUT_MIN_TILE_FLAG) idx = 0;
-        else if (flags & BK_PLAYOUT_MAX_TILE_FLAG) idx = cnt - 1;
-        else idx = int(bk_playout_index(seed, game_id, G.ply, uint32_t(cnt), rng));
-        const int tile = mid ? bk_narrow_select(nw, idx) : bk_legal_select(G.legal, idx, lane);
+    const uint32_t ply0 = G.ply;
+    BkTurn T;
+    bk_turn_resume(G, T, lane, tabs);                    // the stored state may be in the middle of a turn
+    G.meta &= ~(7u << 6);                                // |T| lives in T.nT while the kernel runs
+    G.t01 = 0u; G.t23 = 0u;
+    if (!bk_terminal(G) && T.nT) {
         const int p = bk_cur(G);
-        const uint32_t ply = G.ply;
-        if (!bk_apply_t<true>(G, tile, -1, lane, tabs, ctr, &nw)) break;  // cannot happen: tile came from the legal set
-        mid = ((G.meta >> 6) & 7u) != 0u;
-        if (lane == 0 && ply < BK_HIST_CAP) h16[ply] = uint16_t(tile | (p << 9));
-        if (flags & BK_PLAYOUT_HASH_FLAG) {
-            if (mid) G.legal = bk_narrow_row(nw, lane);
-            h = bk_splitmix64(h ^ bk_digest(G, lane));
-            h = bk_splitmix64(h ^ (uint64_t(p) | (uint64_t(tile) << 8)));
-        }
-        ++steps;
+        bk_playout_turn_moves<HASH>(C, G, T, rng, p, lane, tabs);
+        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr);
     }
-    if (mid) G.legal = bk_narrow_row(nw, lane);
+    while (T.nT == 0 && !bk_terminal(G) && G.ply < C.ply_end) {
+        // turn start: the legal set is the board rows left by the move generator
+        const int p = bk_cur(G);
+        const int cnt = bk_legal_count(G.legal);
+        const int idx = bk_playout_draw(C, G.ply, cnt, rng);
+        int tr, tc;
+        bk_legal_select_rc(G.legal, idx, lane, tr, tc);
+        const int tile = tr * 20 + tc;
+        uint32_t free_, anch;
+        bk_free_anchor(bk_sel4(p, G.o0, G.o1, G.o2, G.o3), G.o0 | G.o1 | G.o2 | G.o3, p, lane, free_, anch);
+        bk_turn_first(G, T, free_, anch, bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3), tr, tc, lane, tabs);
+        if (lane == 0 && G.ply < BK_HIST_CAP) C.h16[G.ply] = uint16_t(tile | (p << 9));
+        G.ply += 1u;
+        if (HASH) { T.last = tile; if ((T.w0 | T.w1 | T.w2) != 0u) bk_playout_digest<HASH>(C, G, T, p, tile, lane); }
+        bk_playout_turn_moves<HASH>(C, G, T, rng, p, lane, tabs);
+        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr);
+    }
+    if (T.nT) bk_turn_materialise(G, T, lane);
     bk_store(&states[g], lane, G);
-    if (lane == 0) { steps_out[g] = steps; hash_out[g] = h; }
+    const int steps = int(G.ply - ply0);
+    if (lane == 0) { steps_out[g] = steps; hash_out[g] = C.h; }
     bk_flush_counters(ctr, uint32_t(steps), lane, counters);
 }
 

@@ -533,7 +533,7 @@ __device__ __forceinline__ uint64_t bk_digest(const BkRegs& G, int lane) {
 // number of legal tiles and the idx-th one in ascending tile order
 __device__ __forceinline__ int bk_legal_count(uint32_t legal) { return bk_warp_sum(__popc(legal)); }
 
-__device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane) {
+__device__ __forceinline__ void bk_legal_select_rc(uint32_t legal, int idx, int lane, int& r, int& c) {
     const int cnt = __popc(legal);
     int incl = cnt;
 #pragma unroll
@@ -549,5 +549,12 @@ __device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane
     // lane j asks: is column j the k-th set bit of that row?  (all lanes cooperate instead of one lane searching)
     const bool hit = ((row >> lane) & 1u) && (__popc(row & ((1u << lane) - 1u)) == k);
     const unsigned col = __ballot_sync(BK_FULL, hit);
-    return src * 20 + (col ? (__ffs(col) - 1) : 0);
+    r = src;
+    c = col ? (__ffs(col) - 1) : 0;
+}
+
+__device__ __forceinline__ int bk_legal_select(uint32_t legal, int idx, int lane) {
+    int r, c;
+    bk_legal_select_rc(legal, idx, lane, r, c);
+    return r * 20 + c;
 }

@@ -115,6 +115,49 @@ def check_stepwise(lib, orc, n_games=4, seed=0, max_plies=10**9, full_every=1):
     return ply
 
 
+def check_playout_cuts(lib, orc, n_games, seed, cuts, apply_after=(), first_game_id=0):
+    """The persistent playout stopped after `cuts` plies (mostly in the middle of a turn, where the turn it keeps
+    in registers has to be written back as Game::apply would have left it) and picked up again: after every cut the
+    FULL state equals the oracle game that replayed the same tiles; optionally some plies go through Game::apply
+    from the cut state (the narrowing cache the playout stored is the one apply continues from); the finished games
+    equal the oracle's uninterrupted traces."""
+    batch = GameBatch(n_games, lib=lib)
+    games = [orc.Game() for _ in range(n_games)]
+    done = [0] * n_games
+    rng = np.random.default_rng(seed)
+
+    def sync():
+        hist = batch.history()
+        for g in range(n_games):
+            for pl, t in hist[g][done[g]:]:
+                assert games[g].current_player() == pl and games[g].apply(int(t))
+            done[g] = len(hist[g])
+        compare_state(batch, games)
+
+    applied = False
+    for i, k in enumerate(cuts):
+        batch.playout(seed=seed, first_game_id=first_game_id, max_plies=k)
+        sync()
+        for _ in range(apply_after[i] if i < len(apply_after) else 0):
+            tiles = []
+            for g in games:
+                lt = g.legal_tiles()
+                tiles.append(-1 if g.is_terminal() else int(lt[rng.integers(len(lt))]))
+            batch.apply(tiles)
+            applied = True
+            sync()
+    batch.playout(seed=seed, first_game_id=first_game_id)
+    sync()
+    assert batch.is_terminal().all()
+    if not applied:
+        hist = batch.history()
+        sc = batch.scores()
+        for g in range(n_games):
+            ref = orc.playout(seed, first_game_id + g, 0)
+            assert [t for _, t in hist[g]] == ref["tiles"].tolist() and list(ref["scores"]) == sc[g].tolist()
+    batch.close()
+
+
 def check_playout(lib, orc, n_games, seed, first_game_id=0, n_check=None, flags=0):
     """Device-resident playout to the end vs the oracle's trace (hash of every ply's full state)."""
     batch = GameBatch(n_games, lib=lib)

@@ -18,6 +18,12 @@ def test_emu_playout_traces(emu_lib, orc):
     parity.check_playout(emu_lib, orc, n_games=4, seed=99, first_game_id=1000)
 
 
+def test_emu_playout_cut_and_resume(emu_lib, orc):
+    """Cuts of 1-7 plies land in the middle of turns in both narrowing forms (more / fewer than 32 surviving placements)."""
+    parity.check_playout_cuts(emu_lib, orc, n_games=3, seed=21, cuts=[1, 1, 1, 2, 3, 1, 5, 7, 1, 1, 37, 1, 2, 90, 1, 3])
+    parity.check_playout_cuts(emu_lib, orc, n_games=2, seed=22, cuts=[1, 2, 6, 1, 30, 1], apply_after=[1, 0, 2, 1, 3, 1])
+
+
 def test_emu_seed_free_traces(emu_lib, orc):
     r = parity.check_playout(emu_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MIN_TILE)
     assert int(r["steps"][0]) == 314
