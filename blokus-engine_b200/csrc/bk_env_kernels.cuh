@@ -158,7 +158,6 @@ __device__ __forceinline__ void bk_playout_turn_moves(BkPlayoutCtx& C, BkRegs& G
         T.tq = (T.tq << 7) | uint32_t(wbit);
         T.nT += 1;
         bk_turn_next(G, T, k, b, lane, tabs);
-        if (lane == 0 && G.ply < BK_HIST_CAP) C.h16[G.ply] = uint16_t(tile | (p << 9));
         G.ply += 1u;
         if (HASH && (T.w0 | T.w1 | T.w2) != 0u) bk_playout_digest<HASH>(C, G, T, p, tile, lane);
         if (HASH) T.last = tile;
@@ -169,15 +168,16 @@ __device__ __forceinline__ void bk_playout_turn_moves(BkPlayoutCtx& C, BkRegs& G
 // is remembered, the turn passes
 template <bool HASH>
 __device__ __forceinline__ void bk_playout_commit(BkPlayoutCtx& C, BkRegs& G, BkTurn& T, int p, int lane,
-                                                  const BkTabs& tabs, BkCounters& ctr) {
+                                                  const BkTabs& tabs, BkCounters& ctr, uint32_t& free_, uint32_t& anch) {
     const int pid = bk_turn_piece(G, T, lane, tabs);
+    bk_turn_record(T, G.ply, p, lane, C.h16);
     const uint32_t rows = bk_window_to_row(G.tw0, G.tw1, G.tw2, T.tr, T.tc, lane);
     const uint32_t clr = ~(1u << pid);
     if (p == 0) { G.o0 |= rows; G.pc0 &= clr; } else if (p == 1) { G.o1 |= rows; G.pc1 &= clr; }
     else if (p == 2) { G.o2 |= rows; G.pc2 &= clr; } else { G.o3 |= rows; G.pc3 &= clr; }
     G.lastlens = (G.lastlens & ~(0xFFu << (8 * p))) | (uint32_t(T.nT) << (8 * p));
     T.nT = 0;
-    bk_advance(G, lane, ctr);
+    bk_advance(G, lane, ctr, free_, anch);            // leaves the next mover's turn-start rows in free_/anch
     if (HASH) bk_playout_digest<HASH>(C, G, T, p, T.last, lane);
 }
 
@@ -201,10 +201,15 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
     bk_turn_resume(G, T, lane, tabs);                    // the stored state may be in the middle of a turn
     G.meta &= ~(7u << 6);                                // |T| lives in T.nT while the kernel runs
     G.t01 = 0u; G.t23 = 0u;
+    uint32_t free_ = 0u, anch = 0u;                      // turn-start rows of the seat to move
+    if (!bk_terminal(G) && T.nT == 0) {
+        const int p = bk_cur(G);
+        bk_free_anchor(bk_sel4(p, G.o0, G.o1, G.o2, G.o3), G.o0 | G.o1 | G.o2 | G.o3, p, lane, free_, anch);
+    }
     if (!bk_terminal(G) && T.nT) {
         const int p = bk_cur(G);
         bk_playout_turn_moves<HASH>(C, G, T, rng, p, lane, tabs);
-        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr);
+        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr, free_, anch);
     }
     while (T.nT == 0 && !bk_terminal(G) && G.ply < C.ply_end) {
         // turn start: the legal set is the board rows left by the move generator
@@ -214,16 +219,16 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
         int tr, tc;
         bk_legal_select_rc(G.legal, idx, lane, tr, tc);
         const int tile = tr * 20 + tc;
-        uint32_t free_, anch;
-        bk_free_anchor(bk_sel4(p, G.o0, G.o1, G.o2, G.o3), G.o0 | G.o1 | G.o2 | G.o3, p, lane, free_, anch);
         bk_turn_first(G, T, free_, anch, bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3), tr, tc, lane, tabs);
-        if (lane == 0 && G.ply < BK_HIST_CAP) C.h16[G.ply] = uint16_t(tile | (p << 9));
         G.ply += 1u;
         if (HASH) { T.last = tile; if ((T.w0 | T.w1 | T.w2) != 0u) bk_playout_digest<HASH>(C, G, T, p, tile, lane); }
         bk_playout_turn_moves<HASH>(C, G, T, rng, p, lane, tabs);
-        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr);
+        if ((T.w0 | T.w1 | T.w2) == 0u) bk_playout_commit<HASH>(C, G, T, p, lane, tabs, ctr, free_, anch);
     }
-    if (T.nT) bk_turn_materialise(G, T, lane);
+    if (T.nT) {
+        bk_turn_record(T, G.ply, bk_cur(G), lane, C.h16);
+        bk_turn_materialise(G, T, lane);
+    }
     bk_store(&states[g], lane, G);
     const int steps = int(G.ply - ply0);
     if (lane == 0) { steps_out[g] = steps; hash_out[g] = C.h; }

@@ -169,17 +169,22 @@ static __device__ __noinline__ uint32_t bk_movegen_rows(uint32_t bk_free, uint32
     return bk_legal & BK_ROWMASK;
 }
 
-__device__ __forceinline__ uint32_t bk_movegen_start(const BkRegs& G, int p, int lane, BkCounters& ctr) {
+// free_/anch: the mover's turn-start rows, handed back because the first tile of the turn narrows against them
+__device__ __forceinline__ uint32_t bk_movegen_start(const BkRegs& G, int p, int lane, BkCounters& ctr, uint32_t& free_,
+                                                     uint32_t& anch) {
     const uint32_t mine = bk_sel4(p, G.o0, G.o1, G.o2, G.o3);
     const uint32_t occ = G.o0 | G.o1 | G.o2 | G.o3;
     const uint32_t pieces = bk_sel4(p, G.pc0, G.pc1, G.pc2, G.pc3);
-    uint32_t free_, anch;
     bk_free_anchor(mine, occ, p, lane, free_, anch);
     if (lane == 0) ctr.movegens += 1u;
     if (lane < BK_NUM_PIECES && ((pieces >> lane) & 1u))
         ctr.crem += uint32_t(c_piece_points[lane]) * uint32_t(c_piece_first_variant[lane + 1] - c_piece_first_variant[lane]);
     if (pieces == 0u || !__any_sync(BK_FULL, anch != 0u)) return 0u;
     return bk_movegen_rows(free_, anch, pieces, lane);
+}
+__device__ __forceinline__ uint32_t bk_movegen_start(const BkRegs& G, int p, int lane, BkCounters& ctr) {
+    uint32_t free_, anch;
+    return bk_movegen_start(G, p, lane, ctr, free_, anch);
 }
 
 struct BkNarrow {
@@ -354,7 +359,7 @@ __device__ __forceinline__ int bk_nth_set_bit(uint32_t mask, int n) {  // n-th (
 // Game::advance_player (game.rs:203-223) as a loop: next seat that is not eliminated and has a
 // legal tile; seats found blocked are eliminated for good.  Move generation is skipped for seats
 // already eliminated — their set is provably empty (boards only fill up), so the result is the same.
-__device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr) {
+__device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr, uint32_t& free_, uint32_t& anch) {
     uint32_t elim = bk_elim(G);
     int cur = bk_cur(G);
     uint32_t legal = 0u;
@@ -363,13 +368,17 @@ __device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr)
         if (elim == 0xFu) break;
         cur = (cur + 1) & 3;
         if ((elim >> cur) & 1u) continue;
-        const uint32_t lg = bk_movegen_start(G, cur, lane, ctr);
+        const uint32_t lg = bk_movegen_start(G, cur, lane, ctr, free_, anch);
         if (!__any_sync(BK_FULL, lg != 0u)) { elim |= 1u << cur; continue; }
         legal = lg;
         break;
     }
     G.legal = legal;
     G.meta = (G.meta & ~0x3Fu) | uint32_t(cur) | (elim << 2);
+}
+__device__ __forceinline__ void bk_advance(BkRegs& G, int lane, BkCounters& ctr) {
+    uint32_t free_, anch;
+    bk_advance(G, lane, ctr, free_, anch);
 }
 
 // Game::apply(tile, piece_to_finish) (game.rs:150-194).  finish < 0 is None.  Returns false (and

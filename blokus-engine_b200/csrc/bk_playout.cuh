@@ -17,7 +17,7 @@
 struct BkTurn {
     uint32_t w0, w1, w2;   // legal set of the turn in progress, window form (warp-uniform); all zero = piece complete
     uint32_t m0, m1, m2;   // compact form only: window masks of this lane's surviving candidate (m0 carries pid << 27), 0 = none
-    uint32_t tq;           // window-bit indices (7 bits each) of the tiles laid this turn, newest in the low bits
+    uint32_t tq;           // window-bit indices (7 bits each) of the turn's tiles AFTER the first (always the centre), newest in the low bits
     int tr, tc;            // T[0]
     int nT;                // |T|
     int last;              // the last tile laid (only kept when a digest per ply is asked for)
@@ -101,7 +101,7 @@ __device__ __forceinline__ void bk_turn_first(BkRegs& G, BkTurn& T, uint32_t fre
     T.w0 = __reduce_or_sync(BK_FULL, L0) & 0x7FFFFFFu;
     T.w1 = __reduce_or_sync(BK_FULL, L1) & ~TW1;
     T.w2 = __reduce_or_sync(BK_FULL, L2);
-    T.tr = tr; T.tc = tc; T.nT = 1; T.tq = 40u;
+    T.tr = tr; T.tc = tc; T.nT = 1; T.tq = 0u;
     T.m0 = T.m1 = T.m2 = 0u;
     G.smask = smask;
     G.tw0 = 0u; G.tw1 = TW1; G.tw2 = 0u;
@@ -167,12 +167,21 @@ __device__ __forceinline__ void bk_turn_materialise(BkRegs& G, const BkTurn& T, 
     if (p == 0) G.o0 |= rows; else if (p == 1) G.o1 |= rows; else if (p == 2) G.o2 |= rows; else G.o3 |= rows;
     G.legal = bk_window_to_row(T.w0, T.w1, T.w2, T.tr, T.tc, lane);
     G.meta = (G.meta & ~(7u << 6)) | (uint32_t(T.nT) << 6);
-    uint32_t t[4] = {0u, 0u, 0u, 0u};
+    uint32_t t[4] = {uint32_t(T.tr * 20 + T.tc), 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 1; i < 4; ++i)
         if (i < T.nT) t[i] = uint32_t(bk_window_tile(int((T.tq >> (7 * (T.nT - 1 - i))) & 127u), T.tr, T.tc));
     G.t01 = t[0] | (t[1] << 16);
     G.t23 = t[2] | (t[3] << 16);
+}
+
+// The turn's tiles go to the move history together: lane i writes the i-th tile of the turn (one store per piece
+// instead of one per tile).  ply = the game's ply count, the turn's tiles included.
+__device__ __forceinline__ void bk_turn_record(const BkTurn& T, uint32_t ply, int p, int lane, uint16_t* __restrict__ h16) {
+    const int sh = 7 * (T.nT - 1 - lane);
+    const int wbit = lane == 0 ? 40 : int((T.tq >> (sh & 31)) & 127u);
+    const uint32_t at = ply - uint32_t(T.nT) + uint32_t(lane);
+    if (lane < T.nT && at < BK_HIST_CAP) h16[at] = uint16_t(bk_window_tile(wbit, T.tr, T.tc) | (p << 9));
 }
 
 // the reverse: pick up a stored state whose turn is in progress
@@ -185,7 +194,7 @@ __device__ __forceinline__ void bk_turn_resume(const BkRegs& G, BkTurn& T, int l
     bk_rows_to_window(G.legal, T.tr, T.tc, lane, T.w0, T.w1, T.w2);
     const uint32_t ts[4] = {G.t01 & 0xFFFFu, G.t01 >> 16, G.t23 & 0xFFFFu, G.t23 >> 16};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 1; i < 4; ++i)
         if (i < T.nT) T.tq = (T.tq << 7) | uint32_t(bk_tile_window_bit(int(ts[i]), T.tr, T.tc));
     bk_turn_load_masks(G, T, tabs);
 }
