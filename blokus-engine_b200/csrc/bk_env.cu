@@ -468,8 +468,9 @@ static int env_playout(bk_env* e, uint64_t seed, uint32_t first_game_id, const u
     }
     BK_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     BK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    // the per-ply state digest is its own instantiation: the plain playout carries neither its registers nor its code
-    if (flags & BK_PLAYOUT_HASH_FLAG)
+    // the per-ply state digest and the tests' seed-free policies are their own instantiation: the plain playout carries
+    // neither their registers nor their code
+    if (flags & (BK_PLAYOUT_HASH_FLAG | BK_PLAYOUT_MIN_TILE_FLAG | BK_PLAYOUT_MAX_TILE_FLAG))
         BK_LAUNCH(k_playout<true>, e->n, 32, e->stream, e->d_states, e->d_hist, e->n, seed, first_game_id, d_ids, max_plies,
                   flags, e->d_i32, e->d_hash, e->d_counters);
     else

@@ -131,16 +131,18 @@ struct BkPlayoutCtx {
 
 template <bool HASH>
 __device__ __forceinline__ void bk_playout_digest(BkPlayoutCtx& C, const BkRegs& G, const BkTurn& T, int p, int tile, int lane) {
-    if (!HASH) return;
+    if (!HASH || !(C.flags & BK_PLAYOUT_HASH_FLAG)) return;
     BkRegs H = G;
     if (T.nT) bk_turn_materialise(H, T, lane);
     C.h = bk_splitmix64(C.h ^ bk_digest(H, lane));
     C.h = bk_splitmix64(C.h ^ (uint64_t(p) | (uint64_t(tile) << 8)));
 }
 
+// CHECKED = the instantiation that also serves the tests' seed-free policies (lowest / highest tile) and the per-ply digest
+template <bool CHECKED>
 __device__ __forceinline__ int bk_playout_draw(const BkPlayoutCtx& C, uint32_t ply, int cnt, BkPlayoutRng& rng) {
-    if (C.flags & BK_PLAYOUT_MIN_TILE_FLAG) return 0;
-    if (C.flags & BK_PLAYOUT_MAX_TILE_FLAG) return cnt - 1;
+    if (CHECKED && (C.flags & BK_PLAYOUT_MIN_TILE_FLAG)) return 0;
+    if (CHECKED && (C.flags & BK_PLAYOUT_MAX_TILE_FLAG)) return cnt - 1;
     return int(bk_playout_index(C.seed, C.game_id, ply, uint32_t(cnt), rng));
 }
 
@@ -150,7 +152,7 @@ __device__ __forceinline__ void bk_playout_turn_moves(BkPlayoutCtx& C, BkRegs& G
                                                       int lane, const BkTabs& tabs) {
     while ((T.w0 | T.w1 | T.w2) != 0u && G.ply < C.ply_end) {
         const int c0 = __popc(T.w0), c1 = __popc(T.w1), cnt = c0 + c1 + __popc(T.w2);
-        const int idx = bk_playout_draw(C, G.ply, cnt, rng);
+        const int idx = bk_playout_draw<HASH>(C, G.ply, cnt, rng);
         int k, wbit;
         uint32_t b;
         bk_turn_pick(T, idx, c0, c1, k, b, wbit);
@@ -215,7 +217,7 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
         // turn start: the legal set is the board rows left by the move generator
         const int p = bk_cur(G);
         const int cnt = bk_legal_count(G.legal);
-        const int idx = bk_playout_draw(C, G.ply, cnt, rng);
+        const int idx = bk_playout_draw<HASH>(C, G.ply, cnt, rng);
         int tr, tc;
         bk_legal_select_rc(G.legal, idx, lane, tr, tc);
         const int tile = tr * 20 + tc;

@@ -154,7 +154,8 @@ __device__ __forceinline__ void bk_turn_pick(const BkTurn& T, int idx, int c0, i
     if (idx < c0) { w = T.w0; k = 0; }
     else if (idx < c0 + c1) { w = T.w1; k = 1; idx -= c0; }
     else { w = T.w2; k = 2; idx -= c0 + c1; }
-    for (int i = 0; i < idx; ++i) w &= w - 1u;           // the sets are small (a handful of tiles)
+#pragma unroll 1                                         // the sets are small (a handful of tiles): no unrolled copies
+    for (int i = 0; i < idx; ++i) w &= w - 1u;
     b = w & (0u - w);
     wbit = 27 * k + __ffs(w) - 1;
 }
