@@ -328,7 +328,7 @@ def main() -> int:
 
     import numpy as np
     import torch
-    from blokus_self_play import GameBatch, probe_int_peak
+    from blokus_self_play import GameBatch, probe_int_peak, PLAYOUT_NEW_GAME
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -372,8 +372,8 @@ def main() -> int:
     d2h_bytes = n * 4 + n * 4 * 4 + n * 360 * 2
 
     def device_step(k: int):
-        batch.reset()
-        batch.lib.check(batch.lib.bk_env_playout(batch._h, SEED + k, first_id, -1, 0))
+        # Game::reset + the playout to the end of every game, ONE launch (BK_PLAYOUT_NEW_GAME: the reset runs inside k_playout)
+        batch.lib.check(batch.lib.bk_env_playout(batch._h, SEED + k, first_id, -1, PLAYOUT_NEW_GAME))
 
     def e2e_collect(lane) -> int:
         """wait for the lane's outstanding step and read its result from the pinned host buffers"""
@@ -387,8 +387,7 @@ def main() -> int:
         lane = lanes[k & 1]
         done = e2e_collect(lane)           # step k-2's results (the other lane is still in flight)
         ids_p, plies_p, scores_p, hist_p = lane["p"]
-        lane["b"].reset()
-        lane["b"].run_playout_raw(SEED + k, ids_p)             # H2D of the ids + the playout, enqueued
+        lane["b"].run_playout_raw(SEED + k, ids_p, flags=PLAYOUT_NEW_GAME)   # H2D of the ids + reset + playout (one launch), enqueued
         lane["b"].fetch_raw_async(plies_p, scores_p, hist_p)   # D2H of plies + scores + histories, enqueued
         lane["busy"] = True
         return done
@@ -527,13 +526,13 @@ def main() -> int:
             "ms_per_step": region_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": "configs[1]: 4096 lockstep random-playout games per GPU, legal-move gen + apply only, "
-                                   "every game reset and played to the end each step",
+                                   "every game reset and played to the end each step (the reset runs inside the playout launch)",
                        "games_per_gpu": n, "moves_per_step": moves / args.steps, "seed": SEED,
                        "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": "global game ids, rank r owns [r*n, (r+1)*n); no data-path collective"},
-            # kernels of this library launched inside the timed regions: device-resident steps (k_reset + k_playout), the
-            # sustained loop (same two), end-to-end steps (k_reset + k_playout + k_scores); the other regions add theirs below
-            "gpu_launches": 2 * args.steps + 2 * int(sus_steps) + 3 * args.steps,
+            # kernels of this library launched inside the timed regions: device-resident steps (k_playout), the
+            # sustained loop (the same), end-to-end steps (k_playout + k_scores); the other regions add theirs below
+            "gpu_launches": args.steps + int(sus_steps) + 2 * args.steps,
             "roofline": {"bound": "int32", "achieved": int_ach, "peak": int_peak, "unit": "lane-ops/s", "frac": int_ach / int_peak,
                          "traffic": traffic, "kernel": "k_playout", "launch_ms": launch_ms,
                          "algorithmic_lane_ops_per_launch": lane_ops_per_launch,

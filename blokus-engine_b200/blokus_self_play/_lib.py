@@ -25,6 +25,7 @@ ERR_STATE = -5
 PLAYOUT_HASH = 1
 PLAYOUT_MIN_TILE = 2
 PLAYOUT_MAX_TILE = 4
+PLAYOUT_NEW_GAME = 8
 
 MODE_SKIP_FORCED = 1
 MODE_FORCE_MULTI_LEAF = 2

@@ -12,6 +12,7 @@
 #define BK_PLAYOUT_HASH_FLAG 1u
 #define BK_PLAYOUT_MIN_TILE_FLAG 2u
 #define BK_PLAYOUT_MAX_TILE_FLAG 4u
+#define BK_PLAYOUT_NEW_GAME_FLAG 8u
 
 // per-game scalars gathered by one kernel for the cheap accessors
 struct BkSummary {
@@ -189,8 +190,13 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
                                            int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
                                            unsigned long long* counters, int g, int lane, const BkTabs& tabs) {
     BkRegs G;
-    bk_load(&states[g], lane, G);
     BkCounters ctr = {0u, 0u};
+    if (flags & BK_PLAYOUT_NEW_GAME_FLAG) {              // Game::reset inside the launch: no k_reset, no state round trip
+        BkCounters fresh = {0u, 0u};                     // (its move generation is not added to the launch's counters,
+        bk_reset(G, lane, fresh);                        //  exactly as when bk_env_reset runs it)
+    } else {
+        bk_load(&states[g], lane, G);
+    }
     BkPlayoutCtx C;
     C.seed = seed; C.game_id = game_id; C.flags = flags; C.h = 0ull;
     C.h16 = hist + size_t(g) * BK_HIST_CAP;
@@ -232,6 +238,8 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
         bk_turn_materialise(G, T, lane);
     }
     bk_store(&states[g], lane, G);
+    if (flags & BK_PLAYOUT_NEW_GAME_FLAG)                    // bk_env_reset clears the history: the rest of the row
+        for (uint32_t i = G.ply + uint32_t(lane); i < BK_HIST_CAP; i += 32u) C.h16[i] = 0;
     const int steps = int(G.ply - ply0);
     if (lane == 0) { steps_out[g] = steps; hash_out[g] = C.h; }
     bk_flush_counters(ctr, uint32_t(steps), lane, counters);

@@ -23,19 +23,6 @@ struct BkTurn {
     int last;              // the last tile laid (only kept when a digest per ply is asked for)
 };
 
-// Every lane loaded the same words of the game record, but the compiler cannot know that: a warp reduction says so
-// (REDUX writes a uniform register), and the scalar side of the game — seat, hand, |T|, ply, the window words, the
-// draws — then stays on the uniform datapath with its own register file instead of competing with the bitboards.
-__device__ __forceinline__ void bk_regs_uniform(BkRegs& G) {
-    G.pc0 = __reduce_or_sync(BK_FULL, G.pc0); G.pc1 = __reduce_or_sync(BK_FULL, G.pc1);
-    G.pc2 = __reduce_or_sync(BK_FULL, G.pc2); G.pc3 = __reduce_or_sync(BK_FULL, G.pc3);
-    G.meta = __reduce_or_sync(BK_FULL, G.meta); G.lastlens = __reduce_or_sync(BK_FULL, G.lastlens);
-    G.t01 = __reduce_or_sync(BK_FULL, G.t01); G.t23 = __reduce_or_sync(BK_FULL, G.t23);
-    G.ply = __reduce_or_sync(BK_FULL, G.ply); G.alive = __reduce_or_sync(BK_FULL, G.alive);
-    G.tw0 = __reduce_or_sync(BK_FULL, G.tw0); G.tw1 = __reduce_or_sync(BK_FULL, G.tw1);
-    G.tw2 = __reduce_or_sync(BK_FULL, G.tw2);
-}
-
 // window form of board rows (inverse of bk_window_to_row)
 __device__ __forceinline__ void bk_rows_to_window(uint32_t row, int tr, int tc, int lane, uint32_t& W0, uint32_t& W1,
                                                   uint32_t& W2) {

@@ -130,6 +130,7 @@ int bk_env_digest(bk_env* env, uint64_t* out);
 #define BK_PLAYOUT_HASH 1u     /* also fold a per-ply state digest into hash_out (parity runs) */
 #define BK_PLAYOUT_MIN_TILE 2u /* policy: always the smallest legal tile (seed-free trace)     */
 #define BK_PLAYOUT_MAX_TILE 4u /* policy: always the largest legal tile  (seed-free trace)     */
+#define BK_PLAYOUT_NEW_GAME 8u /* Game::reset (game.rs:102-114) first, inside the same launch: equals bk_env_reset + bk_env_playout */
 /* Plays every game of the batch forward from its current state until it is terminal or max_plies
  * more tiles were applied (max_plies < 0: to the end), entirely on the device: legal-tile
  * generation, seeded choice, Game::apply, per ply.  Default policy: ascending legal tiles, index

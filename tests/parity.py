@@ -158,6 +158,27 @@ def check_playout_cuts(lib, orc, n_games, seed, cuts, apply_after=(), first_game
     batch.close()
 
 
+def check_playout_new_game(lib, n_games, seed, first_game_id=0):
+    """PLAYOUT_NEW_GAME (Game::reset inside the playout launch) equals reset() followed by playout(), whatever the
+    handle held before: states, histories (cleared past the end), steps and trace hashes."""
+    from blokus_self_play import PLAYOUT_NEW_GAME
+    a = GameBatch(n_games, lib=lib)
+    b = GameBatch(n_games, lib=lib)
+    b.playout(seed=seed + 1, first_game_id=7)                       # leftovers of another batch in b's buffers
+    for flags in (0, PLAYOUT_HASH):
+        a.reset()
+        ra = a.playout(seed=seed, first_game_id=first_game_id, flags=flags)
+        rb = b.playout(seed=seed, first_game_id=first_game_id, flags=flags | PLAYOUT_NEW_GAME)
+        assert np.array_equal(ra["steps"], rb["steps"]) and np.array_equal(ra["hash"], rb["hash"])
+        assert np.array_equal(a.digest(), b.digest()) and a.history() == b.history()
+        assert np.array_equal(a.scores(), b.scores()) and np.array_equal(a.legal_mask(), b.legal_mask())
+    rb = b.playout(seed=seed, first_game_id=first_game_id, max_plies=9, flags=PLAYOUT_NEW_GAME)   # a cut right after the reset
+    a.reset()
+    a.playout(seed=seed, first_game_id=first_game_id, max_plies=9)
+    assert np.array_equal(a.digest(), b.digest()) and a.history() == b.history() and int(rb["steps"].max()) == 9
+    a.close(); b.close()
+
+
 def check_playout(lib, orc, n_games, seed, first_game_id=0, n_check=None, flags=0):
     """Device-resident playout to the end vs the oracle's trace (hash of every ply's full state)."""
     batch = GameBatch(n_games, lib=lib)

@@ -24,6 +24,10 @@ def test_emu_playout_cut_and_resume(emu_lib, orc):
     parity.check_playout_cuts(emu_lib, orc, n_games=2, seed=22, cuts=[1, 2, 6, 1, 30, 1], apply_after=[1, 0, 2, 1, 3, 1])
 
 
+def test_emu_playout_new_game_flag(emu_lib, orc):
+    parity.check_playout_new_game(emu_lib, n_games=3, seed=5, first_game_id=40)
+
+
 def test_emu_seed_free_traces(emu_lib, orc):
     r = parity.check_playout(emu_lib, orc, n_games=1, seed=0, flags=parity.PLAYOUT_MIN_TILE)
     assert int(r["steps"][0]) == 314

@@ -96,6 +96,18 @@ def test_gpu_max_plies_prefix(cuda_lib, orc):
     assert np.array_equal(a.digest(), b.digest()) and a.history() == b.history()
 
 
+def test_gpu_playout_cut_and_resume(cuda_lib, orc):
+    """The turn-structured playout keeps the turn in progress in registers: stopped after 1-7 plies (in the middle of turns,
+    in both narrowing forms) it must leave exactly the state Game::apply would have left — full state against the oracle
+    after every cut, some plies through Game::apply from the cut state, and the oracle's uninterrupted traces at the end."""
+    parity.check_playout_cuts(cuda_lib, orc, n_games=24, seed=21, cuts=[1, 1, 1, 2, 3, 1, 5, 7, 1, 1, 37, 1, 2, 90, 1, 3, 40, 2, 60, 1])
+    parity.check_playout_cuts(cuda_lib, orc, n_games=8, seed=22, cuts=[1, 2, 6, 1, 30, 1, 100, 1], apply_after=[1, 0, 2, 1, 3, 1, 2, 1])
+
+
+def test_gpu_playout_new_game_flag(cuda_lib, orc):
+    parity.check_playout_new_game(cuda_lib, n_games=512, seed=5, first_game_id=40)
+
+
 def test_gpu_playout_65536_games(cuda_lib, orc):
     """16x BASELINE.json config 2's width in one launch: every game ends, scores stay in the rules' range, plies in the
     survey's band, and trace hashes of games spread over the batch equal the oracle's; a resume from a mid-turn cut
