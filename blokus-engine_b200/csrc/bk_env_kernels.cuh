@@ -191,12 +191,8 @@ __device__ __forceinline__ void kb_playout(BkState* __restrict__ states, uint16_
                                            unsigned long long* counters, int g, int lane, const BkTabs& tabs) {
     BkRegs G;
     BkCounters ctr = {0u, 0u};
-    if (flags & BK_PLAYOUT_NEW_GAME_FLAG) {              // Game::reset inside the launch: no k_reset, no state round trip
-        BkCounters fresh = {0u, 0u};                     // (its move generation is not added to the launch's counters,
-        bk_reset(G, lane, fresh);                        //  exactly as when bk_env_reset runs it)
-    } else {
-        bk_load(&states[g], lane, G);
-    }
+    if (flags & BK_PLAYOUT_NEW_GAME_FLAG) bk_reset(G, lane, ctr);     // Game::reset inside the launch (its move generation counts as the launch's work)
+    else bk_load(&states[g], lane, G);
     BkPlayoutCtx C;
     C.seed = seed; C.game_id = game_id; C.flags = flags; C.h = 0ull;
     C.h16 = hist + size_t(g) * BK_HIST_CAP;

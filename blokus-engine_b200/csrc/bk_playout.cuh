@@ -74,7 +74,8 @@ __device__ __forceinline__ void bk_turn_first(BkRegs& G, BkTurn& T, uint32_t fre
     uint32_t L0 = 0u, L1 = 0u, L2 = 0u, smask = 0u;
 #pragma unroll
     for (int ch = 0; ch < BK_NUM_CAND_CHUNKS; ++ch) {
-        if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;  // warp-uniform: no piece of this chunk is held
+        // warp-uniform skip: no piece of this chunk is held (a branch-free scan of all 13 chunks measured 7 % slower)
+        if ((c_cand_chunk_pieces[ch] & pieces) == 0u) continue;
         const int idx = ch * 32 + lane;
         const uint32_t w0 = tabs.w0[idx], m1 = tabs.w1[idx], m2 = tabs.w2[idx];
         const bool fits = ((w0 & NF0) | (m1 & NF1) | (m2 & NF2)) == 0u;
