@@ -45,6 +45,16 @@ __device__ __forceinline__ int bk_tile_window_bit(int t, int tr, int tc) {
     return (t / 20 - tr + 4) * 9 + (t % 20 - tc + 4);
 }
 
+// Chunk form -> compact form (bk_narrow_compact) with a shortcut: when no lane holds more than one survivor — the usual
+// case once a tile or two are laid — every lane simply keeps its own, and the scan / shared-memory exchange is skipped.
+// (The compact form does not ask for the survivors to sit on the low lanes.)
+__device__ __forceinline__ void bk_turn_compact(BkRegs& G, int lane, const BkTabs& tabs) {
+    const int cnt = __popc(G.smask);
+    if (__any_sync(BK_FULL, cnt > 1)) { bk_narrow_compact(G, lane, tabs); return; }
+    G.smask = cnt ? uint32_t((__ffs(G.smask) - 1) * 32 + lane) : BK_CAND_NONE;     // (at most 32 survivors: one per lane)
+    G.alive = BK_NARROW_COMPACT;
+}
+
 __device__ __forceinline__ void bk_turn_load_masks(const BkRegs& G, BkTurn& T, const BkTabs& tabs) {
     T.m0 = T.m1 = T.m2 = 0u;
     if ((G.alive & BK_NARROW_COMPACT) && G.smask != BK_CAND_NONE) {
@@ -95,7 +105,7 @@ __device__ __forceinline__ void bk_turn_first(BkRegs& G, BkTurn& T, uint32_t fre
     G.tw0 = 0u; G.tw1 = TW1; G.tw2 = 0u;
     if ((T.w0 | T.w1 | T.w2) != 0u) {                    // the turn goes on: later tiles re-test survivors only
         G.alive = __reduce_or_sync(BK_FULL, smask);
-        bk_narrow_compact(G, lane, tabs);
+        bk_turn_compact(G, lane, tabs);
         bk_turn_load_masks(G, T, tabs);
     } else {
         G.alive = 0u;                                    // chunk form; bk_turn_piece reads smask
@@ -131,7 +141,7 @@ __device__ __forceinline__ void bk_turn_next(BkRegs& G, BkTurn& T, int k, uint32
     G.smask = smask;
     if ((T.w0 | T.w1 | T.w2) != 0u) {
         G.alive = __reduce_or_sync(BK_FULL, smask);
-        bk_narrow_compact(G, lane, tabs);
+        bk_turn_compact(G, lane, tabs);
         bk_turn_load_masks(G, T, tabs);
     }
 }
