@@ -81,7 +81,7 @@ __device__ __forceinline__ BkTree bk_tree_of(const BkPools& pl, const BkSearchCf
 // large batch gains more from residency: 126 registers at 16 games/SM, 96 at 20 (measured on B200, 8192 games:
 // 2.55e8 -> 3.84e8 -> 4.31e8 sims/s; 1024 games: 1.79e8 -> 1.69e8 -> 1.47e8; 24 and 32 per SM spill and are slower:
 // profiles/r01_ab_mcts_occupancy.log).  The host picks per batch size.
-template <int MINB>
+template <int MINB, bool MODES>
 __global__ void __launch_bounds__(32, MINB)
 k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies,
                 unsigned long long* counters) {
@@ -93,7 +93,7 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
     const int g = blockIdx.x;
     if (g >= n) return;
     const BkTree tr = bk_tree_of(pl, cfg, g);
-    kb_selfplay_stub<(MINB < 16)>(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
+    kb_selfplay_stub<(MINB < 16), MODES>(cfg, states, hist, tr, &pl.hdr[g], pl.pol_off + size_t(g) * (BK_HIST_CAP + 1),
                      pl.pol_tile + size_t(g) * cfg.policy_cap, pl.pol_visits + size_t(g) * cfg.policy_cap, max_plies,
                      counters, g, lane, tabs, wsm);
 }
@@ -538,18 +538,17 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     if (pipe)
         BK_LAUNCH(k_selfplay_stub_pipe, sp->n, 64, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n, max_plies,
                   sp->d_counters);
-    else if (minb >= 20)
-        BK_LAUNCH(k_selfplay_stub<20>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
-                  max_plies, sp->d_counters);
-    else if (minb >= 16)
-        BK_LAUNCH(k_selfplay_stub<16>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
-                  max_plies, sp->d_counters);
-    else if (minb >= 12)
-        BK_LAUNCH(k_selfplay_stub<12>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
-                  max_plies, sp->d_counters);
-    else
-        BK_LAUNCH(k_selfplay_stub<1>, sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n,
-                  max_plies, sp->d_counters);
+    else {
+        // exact mode gets the kernel without the opt-in modes' code (see kb_selfplay_stub)
+#define BK_STUB_LAUNCH(MINB, MODES) BK_LAUNCH((k_selfplay_stub<MINB, MODES>), sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, \
+                                              sp->env->d_hist, sp->n, max_plies, sp->d_counters)
+        const bool modes = sp->dcfg.mode != 0u;
+        if (minb >= 20) { if (modes) BK_STUB_LAUNCH(20, true); else BK_STUB_LAUNCH(20, false); }
+        else if (minb >= 16) { if (modes) BK_STUB_LAUNCH(16, true); else BK_STUB_LAUNCH(16, false); }
+        else if (minb >= 12) { if (modes) BK_STUB_LAUNCH(12, true); else BK_STUB_LAUNCH(12, false); }
+        else { if (modes) BK_STUB_LAUNCH(1, true); else BK_STUB_LAUNCH(1, false); }
+#undef BK_STUB_LAUNCH
+    }
     BK_CUDA(cudaEventRecord(sp->ev1, st));
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaStreamSynchronize(st));

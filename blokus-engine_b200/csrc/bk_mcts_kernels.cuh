@@ -43,6 +43,13 @@
 #define BK_SP_ERR_POLICY_CAP 8u
 #define BK_SP_ERR_APPLY 16u
 
+// Lane src's value for every lane of the one-warp search, as a warp reduction instead of a shuffle: REDUX writes a UNIFORM
+// register, so what depends on the value — the select loop's exit, the next block's address and size, the leaf's parent —
+// stays warp-uniform for the compiler.  With every such value uniform (and the opt-in modes compiled out of the exact
+// kernel) ptxas needs no convergence check (BRA.DIV) before any collective of the simulation loop, keeps the scalar
+// state in uniform registers, and the 20-games-per-SM build fits its 96 registers without spilling.
+#define BK_BCAST(v, src) __reduce_or_sync(BK_FULL, lane == (src) ? (v) : 0u)
+
 struct BkSearchCfg {
     uint32_t sims, sample_moves;
     float frac, alpha;
@@ -185,7 +192,7 @@ __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr
         const int v = __shfl_up_sync(BK_FULL, incl, d);
         if (lane >= d) incl += v;
     }
-    const int n = __shfl_sync(BK_FULL, incl, 31);
+    const int n = int(__reduce_add_sync(BK_FULL, unsigned(cnt)));      // (a reduction, not lane 31's scan value: uniform for the compiler)
     int pos = incl - cnt;
     {
         uint32_t mm = m;
@@ -367,7 +374,7 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
             wi = __reduce_max_sync(BK_FULL, key == kmax ? uint32_t(bi) + 1u : 0u) - 1u;
         }
         const int src = int(wi & 31u);                     // child i lives on lane i % 32
-        tn = __shfl_sync(BK_FULL, b_tn, src);
+        tn = BK_BCAST(b_tn, src);
         e = off + wi;
         if (lane == src) {                                 // the winner's lane holds everything the backup needs
             const int slot = depth & (BK_PATH_CAP - 1);    // a path longer than the cap is reported after the loop
@@ -381,9 +388,9 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
         }
         ++depth;
         if (!BK_TN_EXPANDED(tn)) break;                    // the leaf
-        Np = __shfl_sync(BK_FULL, b_n, src);
-        off = __shfl_sync(BK_FULL, b_off, src);
-        node = __shfl_sync(BK_FULL, b_node, src);
+        Np = BK_BCAST(b_n, src);
+        off = BK_BCAST(b_off, src);
+        node = BK_BCAST(b_node, src);
         n = int(BK_TN_NCHILD(tn));
     }
     BkLeaf lf;
@@ -611,7 +618,9 @@ __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, c
 }
 
 // training_game() (simulation.rs:267-296) with the stub evaluator, up to max_plies plies, on one warp.
-template <bool PF>
+// MODES = false: the exact reference behaviour only — the opt-in modes (forced-ply shortcut, tree reuse) are compiled out,
+// cfg.mode must be 0 (then no header has `reused` set: bk_selfplay_set_mode clears it when the mode is left).
+template <bool PF, bool MODES>
 __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState* __restrict__ states,
                                                  uint16_t* __restrict__ hist, const BkTree& tr, BkSearchHdr* hdr_g,
                                                  uint32_t* pol_off, uint16_t* pol_tile, uint32_t* pol_visits,
@@ -633,11 +642,11 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
     while (!bk_terminal(G) && (max_plies < 0 || plies < max_plies) && hd.err == 0u) {
         BkBlock root;
         bool search = true;
-        if (hd.reused) {                                                               // (opt-in tree reuse)
+        if (MODES && hd.reused) {                                                      // (opt-in tree reuse)
             root = bk_tree_resume(tr, hd, cfg, lane);
         } else {
             hd.n_nodes = 0u; hd.n_entries = 0u; hd.root_visits = 0u; hd.sims_done = 0u;   // fresh tree, :183
-            search = !bk_forced_root(tr, hd, cfg, G, lane);                            // (opt-in shortcut, off by default)
+            search = !(MODES && bk_forced_root(tr, hd, cfg, G, lane));                 // (opt-in shortcut, off by default)
             if (search) bk_tree_expand(tr, hd, cfg, G, nullptr, lane, sm, ctr, root);  // evaluate(root), :184
         }
         if (search) {
@@ -646,14 +655,15 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         }
         if (hd.err) break;
         uint32_t played = 0u;
-        const int action = bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile, pol_visits, lane, &played);
+        const int action = int(__reduce_max_sync(BK_FULL, unsigned(bk_tree_finish_ply(tr, hd, cfg, game_id, G.ply, pol_off, pol_tile,
+                                                                                        pol_visits, lane, &played))));   // (uniform for the compiler)
         const int p = bk_cur(G);
         const uint32_t ply = G.ply;
         if (!bk_apply(G, action, -1, lane, tabs, gctr)) { hd.err |= BK_SP_ERR_APPLY; break; }   // :288
         if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
         ++plies;
         hd.reused = 0u;
-        if ((cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G)) bk_tree_reroot(tr, hd, cfg, played, lane);
+        if (MODES && (cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G)) bk_tree_reroot(tr, hd, cfg, played, lane);
     }
     bk_store(&states[g], lane, G);
     if (lane == 0) {
