@@ -69,7 +69,16 @@ def test_gpu_config2_all_4096_trace_hashes(cuda_lib, orc):
     assert int(r["total_steps"]) == C2["total_plies"]
     live = orc.playout_batch(C2["seed"], 0, 4096, n_threads=os.cpu_count() or 1, want_hash=True)
     assert np.array_equal(live["hashes"], r["hash"].astype(np.uint64)) and live["plies"].tolist() == r["steps"].tolist()
-    b.close()
+    # the kernel bench.py times is the PLAIN instantiation (no per-ply digest) started with BK_PLAYOUT_NEW_GAME (reset inside
+    # the launch): same batch through it — every game's complete move history, final state digest and scores must be those
+    # of the run the oracle just vouched for
+    from blokus_self_play import PLAYOUT_NEW_GAME
+    c = GameBatch(4096, lib=cuda_lib)
+    c.playout(seed=C2["seed"] + 1, first_game_id=99)                  # leftovers of another batch in the buffers
+    rc = c.playout(seed=C2["seed"], first_game_id=0, flags=PLAYOUT_NEW_GAME)
+    assert rc["steps"].tolist() == C2["plies"] and c.scores().tolist() == C2["scores"]
+    assert np.array_equal(c.digest(), b.digest()) and c.history() == b.history()
+    b.close(); c.close()
 
 
 def _check_game_records(game, hist, recs, payoff):
