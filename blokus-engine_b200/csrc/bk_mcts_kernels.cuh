@@ -531,8 +531,8 @@ __device__ __forceinline__ bool bk_tree_reroot(const BkTree& tr, BkSearchHdr& hd
             if (lane >= d) { im += vm; ic += vc; }
         }
         if (m) { newid[id] = base_id + (im - m) + 1u; newoff[id] = base_off + (ic - cnt); }
-        base_id += __shfl_sync(BK_FULL, im, 31);
-        base_off += __shfl_sync(BK_FULL, ic, 31);
+        base_id += __reduce_add_sync(BK_FULL, m);          // (= lane 31's scan values, as reductions: uniform for the compiler)
+        base_off += __reduce_add_sync(BK_FULL, cnt);
     }
     __syncwarp();
     // pass 3: forward copy with pointer rewrite
@@ -663,7 +663,8 @@ __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState
         if (lane == 0 && ply < BK_HIST_CAP) hist[size_t(g) * BK_HIST_CAP + ply] = uint16_t(action | (p << 9));
         ++plies;
         hd.reused = 0u;
-        if (MODES && (cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G)) bk_tree_reroot(tr, hd, cfg, played, lane);
+        if (MODES && (cfg.mode & BK_MODE_TREE_REUSE_FLAG) && !bk_terminal(G))
+            bk_tree_reroot(tr, hd, cfg, __reduce_max_sync(BK_FULL, played), lane);
     }
     bk_store(&states[g], lane, G);
     if (lane == 0) {
