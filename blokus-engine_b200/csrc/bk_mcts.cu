@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32, MINB)
 k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies,
                 unsigned long long* counters) {
     __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
-    __shared__ BkWarpSmem wsm;
+    __shared__ BkWarpSmemStub wsm;
     const BkTabs tabs = bk_stage_tables(smem_tabs);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -105,7 +105,7 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
 __global__ void __launch_bounds__(64, 7)
 k_selfplay_stub_pipe(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies, unsigned long long* counters) {
     __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
-    __shared__ BkWarpSmem wsm;
+    __shared__ BkWarpSmemStub wsm;
     __shared__ BkPathBuf pbs[2];
     __shared__ BkPipeShared ps;
     __shared__ float s_ucb[BK_PIPE_TAB_CAP], s_rcp[BK_PIPE_TAB_CAP];
@@ -532,7 +532,7 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     cudaStream_t st = sp->env->stream;
     BK_CUDA(cudaEventRecord(sp->ev0, st));
     const int per_sm = (sp->n + sp->num_sms - 1) / sp->num_sms;     // games an SM would hold if all were resident
-    const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= 9 ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : 20)));
+    const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= 9 ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : (per_sm <= 20 ? 20 : 28))));
     // exact mode and a batch small enough to be latency bound (<= 9 games per SM): the two-warp pipeline
     const bool pipe = sp->dcfg.mode == 0u && (sp->stub_pipe > 0 || (sp->stub_pipe < 0 && per_sm <= 9 && !sp->stub_min_blocks));
     if (pipe)
@@ -543,7 +543,8 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
 #define BK_STUB_LAUNCH(MINB, MODES) BK_LAUNCH((k_selfplay_stub<MINB, MODES>), sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, \
                                               sp->env->d_hist, sp->n, max_plies, sp->d_counters)
         const bool modes = sp->dcfg.mode != 0u;
-        if (minb >= 20) { if (modes) BK_STUB_LAUNCH(20, true); else BK_STUB_LAUNCH(20, false); }
+        if (minb >= 28 && !modes) BK_STUB_LAUNCH(28, false);
+        else if (minb >= 20) { if (modes) BK_STUB_LAUNCH(20, true); else BK_STUB_LAUNCH(20, false); }
         else if (minb >= 16) { if (modes) BK_STUB_LAUNCH(16, true); else BK_STUB_LAUNCH(16, false); }
         else if (minb >= 12) { if (modes) BK_STUB_LAUNCH(12, true); else BK_STUB_LAUNCH(12, false); }
         else { if (modes) BK_STUB_LAUNCH(1, true); else BK_STUB_LAUNCH(1, false); }

@@ -92,15 +92,19 @@ struct BkSpCounters {  // lane-0 partial sums
     uint32_t sims, applies, entries, nodes;
 };
 
-// per-warp shared scratch
-struct BkWarpSmem {
-    float e[400];
+// per-warp shared scratch.  E_CAP: room for the children's exp(policy) — 400 where an evaluator's policy arrives, 1 in the
+// fixed-prior stub kernels, which never touch it (1.6 KB less shared memory per game: 28 resident games per SM instead of 24)
+template <int E_CAP>
+struct BkWarpSmemT {
+    float e[E_CAP];
     uint16_t tile[400];
     uint32_t path[BK_PATH_CAP];
     uint32_t path_n[BK_PATH_CAP];   // visits / value_sum of the path entries as the select read them
     uint32_t path_w[BK_PATH_CAP];   // (valid only inside one kernel: the backup then needs no reload)
     uint8_t path_tp[BK_PATH_CAP];
 };
+typedef BkWarpSmemT<400> BkWarpSmem;
+typedef BkWarpSmemT<1> BkWarpSmemStub;
 
 // Optional streaming (evict-first) stores for what an expansion writes (-DBK_STREAM_STORES): of the ~10 k
 // child entries and 800 node states a move tree creates only a few are ever read again.  Measured on B200
@@ -163,8 +167,9 @@ __device__ __forceinline__ int bk_frame_index(int r, int c, int cur) {
 // yields no child (the node then stays unexpanded, as in the reference) or a pool overflowed.
 struct BkBlock { uint32_t off, n; };   // child block of the node an expansion created
 
+template <class SM>
 __device__ __forceinline__ uint32_t bk_tree_expand(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
-                                                   const BkRegs& L, const float* policy, int lane, BkWarpSmem& sm,
+                                                   const BkRegs& L, const float* policy, int lane, SM& sm,
                                                    BkSpCounters& ctr, BkBlock& blk, uint32_t slot = BK_NODE_NONE,
                                                    bool store_state = true) {
     blk.off = 0u; blk.n = 0u;
@@ -326,9 +331,9 @@ __device__ __forceinline__ void bk_prefetch_block(const BkTree& tr, uint32_t tn,
 // PF: ask L2 for the node state the leaf step will load, one level ahead.  It pays when a few games per SM are bound by
 // latency (1024 games: the one-warp kernel), and costs 3 % when many resident games are bound by L2 / DRAM traffic (8192 games:
 // the prefetches are half of the DRAM reads), so the high-residency instantiations switch it off.
-template <bool VL, bool PF = true>
+template <bool VL, bool PF = true, class SM>
 __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
-                                                 const BkBlock& root, int lane, BkWarpSmem& sm) {
+                                                 const BkBlock& root, int lane, SM& sm) {
     uint32_t node = 0u;
     uint32_t off = root.off;
     int n = int(root.n);
@@ -409,8 +414,9 @@ __device__ __forceinline__ BkLeaf bk_tree_select(const BkTree& tr, BkSearchHdr& 
 // backpropagate (simulation.rs:164-171): every entry on the path gets +1 visit and the value of the seat
 // to move AT that node (0 for a terminal / unexpanded leaf, node.rs:20).  The visit count and value sum
 // the select read are still current (one simulation in flight per game), so nothing is reloaded.
+template <class SM>
 __device__ __forceinline__ void bk_tree_backup(const BkTree& tr, int depth, const float (&val)[4], int lane,
-                                               const BkWarpSmem& sm) {
+                                               const SM& sm) {
     for (int d = lane; d < depth; d += 32) {
         const uint32_t e = sm.path[d];
         const int tp = int(sm.path_tp[d]);
@@ -588,9 +594,9 @@ __device__ __forceinline__ BkBlock bk_tree_resume(const BkTree& tr, BkSearchHdr&
 
 // One simulation's leaf step for the fixed-prior stub: apply the leaf tile to the parent's state,
 // evaluate (terminal payoff, or stub value + expansion), back up.
-template <bool PF>
+template <bool PF, class SM>
 __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, const BkSearchCfg& cfg,
-                                            const BkBlock& root, int lane, const BkTabs& tabs, BkWarpSmem& sm,
+                                            const BkBlock& root, int lane, const BkTabs& tabs, SM& sm,
                                             BkCounters& gctr, BkSpCounters& ctr) {
     hd.root_visits += 1u;                                                        // simulation.rs:194
     const BkLeaf lf = bk_tree_select<false, PF>(tr, hd, cfg, root, lane, sm);
@@ -620,12 +626,12 @@ __device__ __forceinline__ void bk_sim_stub(const BkTree& tr, BkSearchHdr& hd, c
 // training_game() (simulation.rs:267-296) with the stub evaluator, up to max_plies plies, on one warp.
 // MODES = false: the exact reference behaviour only — the opt-in modes (forced-ply shortcut, tree reuse) are compiled out,
 // cfg.mode must be 0 (then no header has `reused` set: bk_selfplay_set_mode clears it when the mode is left).
-template <bool PF, bool MODES>
+template <bool PF, bool MODES, class SM>
 __device__ __forceinline__ void kb_selfplay_stub(const BkSearchCfg& cfg, BkState* __restrict__ states,
                                                  uint16_t* __restrict__ hist, const BkTree& tr, BkSearchHdr* hdr_g,
                                                  uint32_t* pol_off, uint16_t* pol_tile, uint32_t* pol_visits,
                                                  int max_plies, unsigned long long* counters, int g, int lane,
-                                                 const BkTabs& tabs, BkWarpSmem& sm) {
+                                                 const BkTabs& tabs, SM& sm) {
     BkRegs G;
     bk_load(&states[g], lane, G);
     BkSearchHdr hd;

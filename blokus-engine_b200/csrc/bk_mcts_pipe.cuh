@@ -24,7 +24,9 @@
 #include "bk_mcts_kernels.cuh"
 
 #define BK_TN_TERMINAL(tn) (((tn) >> 22) & 1u)
+#ifndef BK_PIPE_TAB_CAP
 #define BK_PIPE_TAB_CAP 1024      // UCB factor tables up to this many entries are staged in shared memory
+#endif
 
 // -DBK_PIPE_STATS (probe builds only, tools/probe_mcts_pipe.py): cycles each warp spends waiting for the other go to
 // counters[6] (A) / [7] (B), a game's total cycles to [8]; finer sums over all games to g_pipe_stats:
@@ -201,8 +203,9 @@ __device__ __forceinline__ void bk_pipe_backup(const BkTree& tr, int depth, cons
 }
 
 // ---- warp B: the leaf half of a simulation --------------------------------------------------------------------------------
+template <class SM>
 __device__ __forceinline__ void bk_pipe_leaf_worker(const BkSearchCfg& cfg, const BkTree& tr, BkPipeShared& ps, int lane,
-                                                    const BkTabs& tabs, BkWarpSmem& sm, BkCounters& gctr, BkSpCounters& ctr,
+                                                    const BkTabs& tabs, SM& sm, BkCounters& gctr, BkSpCounters& ctr,
                                                     unsigned long long& waited) {
     BkSearchHdr hd;
     hd.n_nodes = ps.n_nodes; hd.n_entries = ps.n_entries; hd.err = 0u;
@@ -342,10 +345,11 @@ __device__ __forceinline__ uint32_t bk_pipe_search(const BkSearchCfg& cfg, const
 
 // training_game() (simulation.rs:267-296) with the stub evaluator on the two-warp pipeline.  Exact mode only
 // (the throughput modes keep the one-warp kernel).  Called by all 64 threads of the game's CTA.
+template <class SM>
 __device__ __forceinline__ void kb_selfplay_stub_pipe(const BkSearchCfg& cfg, BkState* __restrict__ states, uint16_t* __restrict__ hist,
                                                       const BkTree& tr, BkSearchHdr* hdr_g, uint32_t* pol_off, uint16_t* pol_tile,
                                                       uint32_t* pol_visits, int max_plies, unsigned long long* counters, int g,
-                                                      int warp, int lane, const BkTabs& tabs, BkWarpSmem& sm,
+                                                      int warp, int lane, const BkTabs& tabs, SM& sm,
                                                       BkPathBuf (&pbs)[2], BkPipeShared& ps, const float* __restrict__ ucb,
                                                       const float* __restrict__ rcp) {
     BkRegs G;
