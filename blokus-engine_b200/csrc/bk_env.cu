@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(32, 32)
 k_playout(BkState* __restrict__ states, uint16_t* __restrict__ hist, int n, uint64_t seed, uint32_t first_id,
           const uint32_t* __restrict__ ids, int max_plies, uint32_t flags, int32_t* __restrict__ steps_out, uint64_t* __restrict__ hash_out,
           unsigned long long* counters) {
+    // the candidate window masks are copied to shared memory here: this kernel's first-tile scan gathers them on its critical
+    // path, and reading them in place through L1 (bk_global_tables) measured 5.5 % slower (profiles/r02_ab_playout_global_cands.log)
     __shared__ uint32_t smem[BK_TABS_SMEM_WORDS];
     const BkTabs tabs = bk_stage_tables(smem);
     __syncthreads();

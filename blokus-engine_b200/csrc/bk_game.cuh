@@ -101,6 +101,15 @@ __device__ __forceinline__ BkTabs bk_stage_tables(uint32_t* smem) {
     return t;
 }
 
+// The same tables read in place (global memory through L1): for kernels whose candidate scans are a small share of the
+// work, the 5 KB per-CTA copy costs more shared memory (and L1 carve-out) than it saves.  `scratch`: 32 uint16 per warp.
+__device__ __forceinline__ BkTabs bk_global_tables(uint16_t* scratch) {
+    BkTabs t;
+    t.w0 = g_cand_w0; t.w1 = g_cand_w1; t.w2 = g_cand_w2;
+    t.scratch = scratch + 32 * (threadIdx.x >> 5);
+    return t;
+}
+
 __device__ __forceinline__ uint32_t bk_sel4(int p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return p == 0 ? a : (p == 1 ? b : (p == 2 ? c : d));
 }

@@ -85,10 +85,11 @@ template <int MINB, bool MODES>
 __global__ void __launch_bounds__(32, MINB)
 k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies,
                 unsigned long long* counters) {
-    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    // candidate window masks read in place (global memory through L1): the 5 KB per-CTA copy capped residency at 24 games
+    // per SM; without it 28 fit and the 8192-game batch runs 30 % faster (profiles/r02_ab_mcts_stub_global_cands.log)
+    __shared__ uint16_t cand_scratch[32];
     __shared__ BkWarpSmemStub wsm;
-    const BkTabs tabs = bk_stage_tables(smem_tabs);
-    __syncthreads();
+    const BkTabs tabs = bk_global_tables(cand_scratch);
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
@@ -104,12 +105,14 @@ k_selfplay_stub(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, in
 // like, only 5 CTAs fit an SM and 1024 games run in two waves (measured: 1.55 s against 1.26 s for the one-warp kernel).
 __global__ void __launch_bounds__(64, 7)
 k_selfplay_stub_pipe(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, int max_plies, unsigned long long* counters) {
-    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    // candidate window masks straight from global memory (L1): without the 5 KB per-CTA copy the 1024-game run is 2 %
+    // faster (profiles/r02_ab_mcts_global_cands.log)
+    __shared__ uint16_t cand_scratch[32 * 2];
     __shared__ BkWarpSmemStub wsm;
     __shared__ BkPathBuf pbs[2];
     __shared__ BkPipeShared ps;
     __shared__ float s_ucb[BK_PIPE_TAB_CAP], s_rcp[BK_PIPE_TAB_CAP];
-    const BkTabs tabs = bk_stage_tables(smem_tabs);
+    const BkTabs tabs = bk_global_tables(cand_scratch);
     // the UCB factor tables (sims + 2 and sims + 3 floats) in shared memory when they fit
     const bool tabs_fit = cfg.sims + 3u <= BK_PIPE_TAB_CAP;
     if (tabs_fit)
@@ -225,10 +228,9 @@ __global__ void k_sp_count(BkPools pl, int n, int32_t* __restrict__ counts) {
 
 __global__ void __launch_bounds__(32)
 k_sp_step(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* value, unsigned long long* counters) {
-    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ uint16_t cand_scratch[32];
     __shared__ BkWarpSmem wsm;
-    const BkTabs tabs = bk_stage_tables(smem_tabs);
-    __syncthreads();
+    const BkTabs tabs = bk_global_tables(cand_scratch);     // one simulation per launch: a 5 KB table copy per game would cost more than it saves
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
@@ -239,10 +241,9 @@ k_sp_step(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* 
 
 __global__ void __launch_bounds__(32)
 k_sp_step_vl(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const float* value, unsigned long long* counters) {
-    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ uint16_t cand_scratch[32];
     __shared__ BkWarpSmem wsm;
-    const BkTabs tabs = bk_stage_tables(smem_tabs);
-    __syncthreads();
+    const BkTabs tabs = bk_global_tables(cand_scratch);     // one simulation per launch: a 5 KB table copy per game would cost more than it saves
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
@@ -253,10 +254,9 @@ k_sp_step_vl(BkSearchCfg cfg, BkPools pl, int n, const float* policy, const floa
 
 __global__ void __launch_bounds__(32)
 k_sp_end(BkSearchCfg cfg, BkPools pl, BkState* states, uint16_t* hist, int n, unsigned long long* counters) {
-    __shared__ uint32_t smem_tabs[BK_TABS_SMEM_WORDS];
+    __shared__ uint16_t cand_scratch[32];
     __shared__ BkWarpSmem wsm;
-    const BkTabs tabs = bk_stage_tables(smem_tabs);
-    __syncthreads();
+    const BkTabs tabs = bk_global_tables(cand_scratch);     // one simulation per launch: a 5 KB table copy per game would cost more than it saves
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     if (g >= n) return;
