@@ -543,7 +543,7 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
 #define BK_STUB_LAUNCH(MINB, MODES) BK_LAUNCH((k_selfplay_stub<MINB, MODES>), sp->n, 32, st, sp->dcfg, pools_of(sp), sp->env->d_states, \
                                               sp->env->d_hist, sp->n, max_plies, sp->d_counters)
         const bool modes = sp->dcfg.mode != 0u;
-        if (minb >= 28 && !modes) BK_STUB_LAUNCH(28, false);
+        if (minb >= 28) { if (modes) BK_STUB_LAUNCH(28, true); else BK_STUB_LAUNCH(28, false); }
         else if (minb >= 20) { if (modes) BK_STUB_LAUNCH(20, true); else BK_STUB_LAUNCH(20, false); }
         else if (minb >= 16) { if (modes) BK_STUB_LAUNCH(16, true); else BK_STUB_LAUNCH(16, false); }
         else if (minb >= 12) { if (modes) BK_STUB_LAUNCH(12, true); else BK_STUB_LAUNCH(12, false); }

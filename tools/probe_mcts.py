@@ -7,6 +7,8 @@ LIB = Lib(os.environ['BK_LIB']) if os.environ.get('BK_LIB') else None
 CASES = [(8192, 12)] if os.environ.get('BK_BIG') else [(1024, -1)] if os.environ.get('BK_FULLGAME') else [(1024, 16)] if os.environ.get('BK_QUICK') else [(1024, 4), (1024, 16), (4096, 8), (8192, 8)]
 cfg = Config(sims_per_move=800, sample_moves=30, c_base=19652, c_init=1.25, dirichlet_alpha=0.03,
              exploration_fraction=0.25, seed=1)
+if os.environ.get('BK_N'):
+    CASES = [(int(os.environ['BK_N']), int(os.environ.get('BK_PLIES', '8')))]
 for n, plies in CASES:
     sp = SelfPlay(n, cfg, lib=LIB, max_children_per_game=int(os.environ.get('BK_CAP', '0')))
     c0 = sp.counters()
