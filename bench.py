@@ -568,7 +568,7 @@ def main() -> int:
                 "config": "configs[2]: 1024 games per GPU, 800 sims/move, fixed uniform priors (stub evaluator), Dirichlet "
                           "alpha 0.03 frac 0.25, sample_moves 30; " + ("complete games" if args.mcts_plies < 0 else f"first {args.mcts_plies} plies"),
                 "sims": mcts_sims, "plies_searched": mcts_plies, "finished_games": mcts_done, "kernel_ms": mcts_ms,
-                "kernel": "k_selfplay_stub (one launch: every ply's root expansion, noise, 800 sims, action, apply)",
+                "kernel": "k_selfplay_stub_pipe at <= 9 games per SM (two warps per game), k_selfplay_stub<MINB> above — one launch: every ply's root expansion, noise, 800 sims, action, apply",
                 "e2e": {"value": mcts_e2e_sims / mcts_e2e_s, "unit": "sims/s", "seconds": mcts_e2e_s,
                         "h2d_bytes_per_step": mcts["e2e_h2d_bytes"], "d2h_bytes_per_step": mcts_d2h / world,
                         "what": "bk_selfplay_reset + bk_selfplay_run_stub + the finished-game training tuples (packed policy records, "
