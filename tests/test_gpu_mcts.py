@@ -122,7 +122,7 @@ def test_gpu_skip_forced_stub_full_games(cuda_lib, orc):
 
 
 def test_gpu_config5_shard_width(cuda_lib, orc):
-    """BASELINE.json config 5's per-GPU share at full width: 8192 games x 800 sims (the 20-games-per-SM instantiation of
+    """BASELINE.json config 5's per-GPU share at full width: 8192 games x 800 sims (the 28-games-per-SM instantiation of
     the stub kernel), two plies — visit-sum invariant for every game, and a 48-game batch at global id 3000 (the
     all-registers instantiation) reproduces that slice: results depend on the global game id only."""
     from blokus_self_play import SelfPlay, Config
@@ -242,3 +242,45 @@ def test_gpu_pipeline_tables_beyond_shared_memory(cuda_lib):
     from test_emu_mcts import _pipeline_equals_one_warp_kernel
     _pipeline_equals_one_warp_kernel(cuda_lib, 8, 1100, 3)
     _pipeline_equals_one_warp_kernel(cuda_lib, 4, 5000, 1)
+
+
+def test_gpu_one_warp_instantiations_agree(cuda_lib):
+    """Every residency instantiation of the one-warp search kernel (1 / 12 / 16 / 20 / 28 games per SM, chosen by batch
+    size in production, forced here through BK_STUB_MIN_BLOCKS) plays the same games: exact mode against the two-warp
+    pipeline, and the opt-in modes (forced-ply shortcut + tree reuse) against each other — histories, policy records
+    and payoffs, 40 plies at 160 sims."""
+    import os
+    from blokus_self_play import SelfPlay, Config, MODE_SKIP_FORCED, MODE_TREE_REUSE
+    cfg = Config(**dict(CONFIG3, sims_per_move=160, dirichlet_alpha=0.3, seed=77))
+
+    def run(min_blocks, flags):
+        old = os.environ.get("BK_STUB_MIN_BLOCKS")
+        if min_blocks:
+            os.environ["BK_STUB_MIN_BLOCKS"] = str(min_blocks)       # read by bk_selfplay_create
+        try:
+            sp = SelfPlay(24, cfg, first_game_id=500, lib=cuda_lib)
+        finally:
+            if min_blocks:
+                if old is None:
+                    del os.environ["BK_STUB_MIN_BLOCKS"]
+                else:
+                    os.environ["BK_STUB_MIN_BLOCKS"] = old
+        if flags:
+            sp.set_mode(flags, 1)
+        sp.run_stub(40)
+        out = (sp.env.history(), sp.policy_records(), sp.env.payoff().tolist())
+        sp.close()
+        return out
+
+    def same(a, b):
+        assert a[0] == b[0] and a[2] == b[2]
+        for ra, rb in zip(a[1], b[1]):
+            assert len(ra) == len(rb)
+            for (t1, v1), (t2, v2) in zip(ra, rb):
+                assert np.array_equal(t1, t2) and np.array_equal(v1, v2)
+
+    for flags in (0, MODE_SKIP_FORCED | MODE_TREE_REUSE):
+        base = run(0, flags)                 # the library's own choice: the pipeline in exact mode, <1, true> with modes
+        assert all(len(h) >= 40 for h in base[0])
+        for mb in (1, 12, 16, 20, 28):
+            same(base, run(mb, flags))
