@@ -31,6 +31,8 @@ struct bk_selfplay {
     uint32_t* d_slot_base = nullptr;  // [n + 1]: first dense evaluator row of each game's outstanding positions (+ total)
     bool use_vl = false;
     int num_sms = 148;
+    int pipe_resident = 7;            // CTAs of k_selfplay_stub_pipe an SM holds (occupancy API at create)
+    int full_resident = 8;            // same for the all-registers one-warp instantiations k_selfplay_stub<1, *>
     int stub_min_blocks = 0;          // 0 = choose by batch size; BK_STUB_MIN_BLOCKS in the environment overrides (probes)
     int stub_pipe = -1;               // -1 = two-warp pipeline for small exact-mode batches; BK_STUB_PIPE=0/1 forces it off/on
     uint32_t* d_pol_off = nullptr;    // [n][BK_HIST_CAP + 1]
@@ -371,6 +373,13 @@ int bk_selfplay_create(int n_games, int device, const bk_config* cfg, uint32_t f
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) sp->num_sms = prop.multiProcessorCount;
         if (const char* e = getenv("BK_STUB_MIN_BLOCKS")) sp->stub_min_blocks = atoi(e);
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_selfplay_stub_pipe, 64, 0) == cudaSuccess && resident > 0)
+            sp->pipe_resident = resident;
+        int r0 = 0, r1 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r0, k_selfplay_stub<1, false>, 32, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r1, k_selfplay_stub<1, true>, 32, 0) == cudaSuccess && r0 > 0 && r1 > 0)
+            sp->full_resident = r0 < r1 ? r0 : r1;
     }
 #endif
 #ifdef BK_WARP_EMU
@@ -532,9 +541,13 @@ int bk_selfplay_run_stub(bk_selfplay* sp, int max_plies) {
     cudaStream_t st = sp->env->stream;
     BK_CUDA(cudaEventRecord(sp->ev0, st));
     const int per_sm = (sp->n + sp->num_sms - 1) / sp->num_sms;     // games an SM would hold if all were resident
-    const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= 9 ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : (per_sm <= 20 ? 20 : 28))));
+    // (a batch one game per SM slot too large for an instantiation runs in two waves: 1300 games took 78 ms for 12 plies on
+    // <1> — 8 resident per SM — against 47 ms on <12>, profiles/r02_ab_mcts_pipe_threshold.log)
+    const int minb = sp->stub_min_blocks ? sp->stub_min_blocks : (per_sm <= (sp->full_resident < 9 ? sp->full_resident : 9) ? 1 : (per_sm <= 12 ? 12 : (per_sm <= 16 ? 16 : (per_sm <= 20 ? 20 : 28))));
     // exact mode and a batch small enough to be latency bound (<= 9 games per SM): the two-warp pipeline
-    const bool pipe = sp->dcfg.mode == 0u && (sp->stub_pipe > 0 || (sp->stub_pipe < 0 && per_sm <= 9 && !sp->stub_min_blocks));
+    // ... and only while every game is resident at once (one CTA per game: a second wave would double the run)
+    const bool pipe = sp->dcfg.mode == 0u && (sp->stub_pipe > 0 || (sp->stub_pipe < 0 && per_sm <= 9 && per_sm <= sp->pipe_resident &&
+                                                                    !sp->stub_min_blocks));
     if (pipe)
         BK_LAUNCH(k_selfplay_stub_pipe, sp->n, 64, st, sp->dcfg, pools_of(sp), sp->env->d_states, sp->env->d_hist, sp->n, max_plies,
                   sp->d_counters);
