@@ -1,3 +1,7 @@
+#!/bin/bash
+# Record of the A/B that made in-place candidate tables the default (profiles/r02_ab_mcts_stub_global_cands.log):
+# '' = the library with the 5 KB shared-memory copy per game, '_sgc' = the same sources built with the (since removed)
+# -DBK_STUB_GLOBAL_CANDS switch, i.e. today's default.  To repeat it, build the old side from commit 14cbde9.
 for v in "" _sgc; do
  f=blokus-engine_b200/lib/libblokus_b200$v.so
  for mb in 20 28; do
